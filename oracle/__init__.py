@@ -1,0 +1,28 @@
+"""CPU oracle for the camera_linearity hot path.  TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+
+This package is a NumPy restatement of the reference algorithm (samivout/camera_linearity,
+``/root/reference/modules``) for the four kernels K1..K4 of SURVEY.md section 8, following the
+reference's own operation order so that results are bit-identical to "reference + the
+documented repair set R1..R9" (DESIGN.md section 3).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it, and only as the checker / the timed CPU baseline.
+Nothing under ``camera_linearity_b200/`` imports it; the product path fails loudly when the
+CUDA library is missing (``camera_linearity_b200/_lib.py``).
+
+Parity status of this oracle (see DESIGN.md section 3 and ``tests/test_oracle_golden.py``):
+
+* K4 (calibration loss), K3 (Welford, ICRF=None), single-channel K1, the Gaussian weight and the
+  Measurand operators are pinned against the UNMODIFIED reference functions run in the build
+  container (``tests/golden/make_golden.py`` imports them from ``/root/reference`` and the
+  outputs are committed under ``tests/golden/``), plus the survey's known-answer values.
+* K2 (HDR merge), multi-channel K1, bad-pixel filter, flat-field normalisation and Welford with
+  an ICRF do not run at reference HEAD (defects D1..D13).  For those the golden vectors are
+  produced by driving the reference's own working pieces (``apply_gaussian_weight``,
+  ``_linearize_single``, ``scipy.ndimage.median_filter``) through the literal formulae of
+  ``exposure_series.py:388-394`` / ``measurand.py:586-602`` with repairs R1..R9 -- i.e. the
+  pin is "reference pieces + repair set", not an end-to-end reference run.  The reference's
+  own tests hold no golden vectors for any of K1..K4.
+"""
+
+from . import linearize, hdr_merge, welford, icrf_energy  # noqa: F401
