@@ -1,0 +1,492 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: fused HDR merge throughput in Gpix*exposures/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1]
+
+One "step" = one fused HDR merge of one synthetic exposure stack (cfg2 of BASELINE.json /
+SURVEY.md 8d by default: 16 exposures 3840x2160x3 uint8 + float64 uncertainty images, dark
+frames for the exposures >= 0.05 s, flat field).  N > 1 (torchrun): every rank merges its own
+stack -- stacks are independent units, no data-path collective -- so scaling is "weak" and
+`value` = total pix*exposures of all ranks / max-over-ranks time.
+
+`value`   : inputs resident in HBM, CUDA-event timed, per rank max.
+`e2e`     : the same merge through the public API (ExposureSeries.process_HDR_image) from pinned
+            HOST buffers, host->device copies and the device->host read of the result inside the
+            timed region.
+`roofline`: algorithmic bytes of the merge kernel / its CUDA-event duration vs the measured HBM
+            peak (MEASURED_PEAKS.json, else the 6.65 TB/s fallback of B200_PROFILING.md).
+`cpu_baseline`: the NumPy oracle port of the reference timed on a bounded row crop of the same
+            workload on this box's host cores.
+--impl reference: the oracle port (the reference is pure Python/NumPy and does not run at HEAD,
+            see DESIGN.md) on all host cores, row tiles in a process pool.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (H, W, C, N, t0, ratio, corrections)
+    "cfg1": dict(H=1536, W=2048, C=3, N=5, t0=0.005, ratio=2.0, corrections=False,
+                 label="cfg1: 5-exposure 2048x1536x3 uint8 + f64 std, fixed ICRF"),
+    "cfg2": dict(H=2160, W=3840, C=3, N=16, t0=0.001, ratio=1.6, corrections=True,
+                 label="cfg2: 16-exposure 3840x2160x3 uint8 + f64 std, dark frames (t>=0.05s) + flat field"),
+}
+DARK_THRESHOLD = 0.05
+KERNEL = 3
+FF_MID = 0.2
+
+
+def exposures_of(wl):
+    return wl["t0"] * wl["ratio"] ** np.arange(wl["N"])
+
+
+def icrf_tables(C):
+    x = np.linspace(0, 1, 256)
+    icrf = np.stack([x ** (2.0 + 0.1 * c) for c in range(C)], axis=1)
+    diff = np.stack([np.gradient(icrf[:, c], 2 / 255) for c in range(C)], axis=1)
+    return icrf, diff
+
+
+def algorithmic_bytes(wl, n_dark):
+    n = wl["H"] * wl["W"] * wl["C"]
+    b = wl["N"] * n * 9 + n_dark * n * 1 + n * 16
+    if wl["corrections"]:
+        b += n * 9
+    return b
+
+
+# ----------------------------------------------------------------------------- synthetic data
+def make_stack_numpy(wl, rows, seed):
+    """Host (NumPy) synthetic crop of `rows` rows: same generator family as the device one."""
+    rng = np.random.default_rng(seed)
+    H, W, C = rows, wl["W"], wl["C"]
+    t = exposures_of(wl)
+    rad = rng.uniform(0, 1, (H, W, C)) * 25
+    dn = [np.rint(255 * np.clip(rad * tk, 0, 1) ** (1 / 2.2)).astype(np.uint8) for tk in t]
+    std = [rng.uniform(0.002, 0.02, (H, W, C)) for _ in t]
+    darks = [None] * wl["N"]
+    flat = flat_std = None
+    if wl["corrections"]:
+        for k, tk in enumerate(t):
+            if tk >= DARK_THRESHOLD:
+                d = rng.poisson(2.0, (H, W, C)).astype(np.uint8)
+                hot = rng.uniform(size=d.shape) < 0.001
+                d[hot] = rng.integers(40, 200, int(hot.sum()))
+                darks[k] = d
+        flat = np.clip(np.rint(rng.normal(180, 6, (H, W, C))), 1, 255).astype(np.uint8)
+        flat_std = rng.uniform(0.001, 0.01, (H, W, C))
+    return dict(dn=dn, std=std, t=t, darks=darks, flat=flat, flat_std=flat_std)
+
+
+def make_stack_device(wl, seed, dev):
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    H, W, C = wl["H"], wl["W"], wl["C"]
+    t = exposures_of(wl)
+    rad = torch.rand((H, W, C), generator=g, device=dev, dtype=torch.float64) * 25
+    dn, std, darks = [], [], []
+    for tk in t:
+        dn.append(torch.round(255 * torch.clamp(rad * tk, 0, 1) ** (1 / 2.2)).to(torch.uint8))
+        std.append(torch.rand((H, W, C), generator=g, device=dev, dtype=torch.float64) * 0.018 + 0.002)
+    flat = flat_std = None
+    for tk in t:
+        if wl["corrections"] and tk >= DARK_THRESHOLD:
+            d = torch.poisson(torch.full((H, W, C), 2.0, device=dev), generator=g).to(torch.uint8)
+            hot = torch.rand((H, W, C), generator=g, device=dev) < 0.001
+            d[hot] = torch.randint(40, 200, (int(hot.sum()),), generator=g, device=dev, dtype=torch.uint8)
+            darks.append(d)
+        else:
+            darks.append(None)
+    if wl["corrections"]:
+        flat = torch.clamp(torch.round(torch.randn((H, W, C), generator=g, device=dev) * 6 + 180), 1, 255).to(torch.uint8)
+        flat_std = torch.rand((H, W, C), generator=g, device=dev, dtype=torch.float64) * 0.009 + 0.001
+    del rad
+    return dict(dn=dn, std=std, t=t, darks=darks, flat=flat, flat_std=flat_std)
+
+
+# ----------------------------------------------------------------------------- CPU (oracle) arm
+_CROP_CACHE = {}
+
+
+def _oracle_merge_crop(args):
+    """Merge one synthetic row crop with the NumPy oracle; returns the merge time only (the crop is
+    generated once per (worker, seed) and cached, so generation stays outside the timing)."""
+    wl_name, rows, seed = args
+    wl = WORKLOADS[wl_name]
+    from oracle import hdr_merge as om
+    key = (wl_name, rows, seed)
+    if key not in _CROP_CACHE:
+        data = make_stack_numpy(wl, rows, seed)
+        if wl["corrections"]:
+            data["dark_val"] = [None if d is None else om.dark_value_image(d, 1.0) for d in data["darks"]]
+            data["flat_val"] = data["flat"] / 255.0
+        _CROP_CACHE[key] = data
+    data = _CROP_CACHE[key]
+    icrf, diff = icrf_tables(wl["C"])
+    t0 = time.perf_counter()
+    om.hdr_merge(data["dn"], data["std"], data["t"], icrf, diff, darks=data.get("dark_val"),
+                 dark_threshold=DARK_THRESHOLD, kernel=KERNEL, flat_val=data.get("flat_val"),
+                 flat_std=data["flat_std"], roi=(0, rows, 0, wl["W"]))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_single(wl_name, rows=96):
+    wl = WORKLOADS[wl_name]
+    dt = _oracle_merge_crop((wl_name, rows, 1234))
+    pix_exp = rows * wl["W"] * wl["N"]
+    return dict(value=pix_exp / dt / 1e9, unit="Gpix*exposures/s", cores=1, kind="port",
+                sample=f"oracle (NumPy port of the reference + repairs R1-R8) on a {rows}-row crop "
+                       f"({rows}x{wl['W']}x{wl['C']}, {wl['N']} exposures) of the workload, {dt:.2f} s, 1 core")
+
+
+def run_reference_arm(args, wl_name):
+    """`--impl reference`: the oracle port on all host cores.  Each step = one bounded row crop per
+    worker process (the reference's NumPy code is single-threaded; row tiles are independent)."""
+    import multiprocessing as mp
+    wl = WORKLOADS[wl_name]
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    rows = 48
+    jobs = [(wl_name, rows, 100 + i) for i in range(cores)]
+    times = []
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_oracle_merge_crop, jobs)            # untimed: generates and caches the crops
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_oracle_merge_crop, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    pix_exp_step = cores * rows * wl["W"] * wl["N"]
+    value = pix_exp_step * len(times) / total / 1e9
+    sample = (f"per step: {cores} worker processes x one {rows}-row crop ({rows}x{wl['W']}x{wl['C']}, "
+              f"{wl['N']} exposures, dark frames + flat field as in the workload) through the NumPy oracle port "
+              f"of the reference (+ repairs R1-R8); wall time of the parallel map, inputs pre-generated")
+    line = {
+        "impl": "reference", "metric": "HDR merge throughput", "value": value, "unit": "Gpix*exposures/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "sample_rows_per_worker": rows, "workers": cores},
+        "cpu_baseline": {"value": value, "unit": "Gpix*exposures/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Gpix*exposures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = f"/tmp/camlin_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.out,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.out.close()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in open(self.path).read().strip().splitlines():
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def hbm_peak():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        try:
+            return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- ours
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import camera_linearity_b200 as cl
+    from camera_linearity_b200 import _lib, ops, parallel
+
+    rank, world, local = parallel.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    cl.GlobalSettings.configure(IM_SIZE_X=wl["H"], IM_SIZE_Y=wl["W"], DARK_THRESHOLD=DARK_THRESHOLD,
+                                MEDIAN_FILTER_KERNEL_SIZE=KERNEL, FF_MID_PERCENTAGE=FF_MID)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    data = make_stack_device(wl, 1000 + rank, dev)
+    icrf_np, diff_np = icrf_tables(wl["C"])
+    icrf, diff = torch.from_numpy(icrf_np).to(dev), torch.from_numpy(diff_np).to(dev)
+    t = [float(x) for x in data["t"]]
+    n_dark = sum(d is not None for d in data["darks"])
+    out = (torch.empty((wl["H"], wl["W"], wl["C"]), dtype=torch.float64, device=dev),
+           torch.empty((wl["H"], wl["W"], wl["C"]), dtype=torch.float64, device=dev))
+    roi = cl.measurand._flat_roi()
+
+    def step():
+        means = None
+        if data["flat"] is not None:
+            means = ops.flat_roi_means(data["flat"], data["flat_std"], roi)
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        ops.hdr_merge(data["dn"], data["std"], t, icrf, diff, darks=data["darks"], dark_threshold=DARK_THRESHOLD,
+                      median_kernel=KERNEL, flat=data["flat"], flat_std=data["flat_std"], flat_means=means,
+                      algo=args.algo, out=out)
+        ev1.record()
+        return ev0, ev1
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    start = torch.cuda.Event(enable_timing=True)
+    stop = torch.cuda.Event(enable_timing=True)
+    start.record()
+    kernel_events = [step() for _ in range(args.steps)]
+    stop.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - launches0
+    total_ms = start.elapsed_time(stop)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    pix_exp = wl["H"] * wl["W"] * wl["N"]
+    value = world * pix_exp * args.steps / (total_ms * 1e-3) / 1e9
+
+    # ---- e2e: public API from pinned host buffers, H2D + D2H inside the timed region ----
+    host = {k: [None if x is None else x.cpu().pin_memory() for x in data[k]] for k in ("dn", "std", "darks")}
+    host_flat = None if data["flat"] is None else data["flat"].cpu().pin_memory()
+    host_flat_std = None if data["flat_std"] is None else data["flat_std"].cpu().pin_memory()
+    out_host = (torch.empty(out[0].shape, dtype=torch.float64).pin_memory(),
+                torch.empty(out[0].shape, dtype=torch.float64).pin_memory())
+    del data, out
+    torch.cuda.empty_cache()
+    feats = lambda tk, subject: {"illumination": "bf", "magnification": "10x", "exposure": tk, "subject": subject}
+
+    def e2e_step():
+        sets = [cl.ImageSet(features=feats(t[k], "s"), measurand=cl.Measurand(None, host["std"][k].to(dev, non_blocking=True)))
+                for k in range(wl["N"])]
+        for k, s in enumerate(sets):
+            s._dn = host["dn"][k].to(dev, non_blocking=True)
+        dark_sets = []
+        for k, d in enumerate(host["darks"]):
+            if d is not None:
+                ds = cl.ImageSet(features=feats(t[k], "dark"), measurand=cl.Measurand(None, None))
+                ds._dn = d.to(dev, non_blocking=True)
+                dark_sets.append(ds)
+        flats = []
+        if host_flat is not None:
+            fs = cl.ImageSet(features=feats(0.0, "flat"), measurand=cl.Measurand(None, host_flat_std.to(dev, non_blocking=True)))
+            fs._dn = host_flat.to(dev, non_blocking=True)
+            flats.append(fs)
+        series = cl.ExposureSeries(input_image_sets=sets)
+        series.process_HDR_image(icrf, diff, dark_list=dark_sets, flat_list=flats, algo=args.algo)
+        m = series.merged_image_set.measurand
+        out_host[0].copy_(m.val, non_blocking=True)
+        out_host[1].copy_(m.std, non_blocking=True)
+
+    n_e2e = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+    tm = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    e2e_value = world * pix_exp * n_e2e / (float(tm.item()) * 1e-3) / 1e9
+    n_samp = wl["H"] * wl["W"] * wl["C"]
+    h2d = wl["N"] * n_samp * 9 + n_dark * n_samp + (n_samp * 9 if wl["corrections"] else 0)
+    d2h = n_samp * 16
+    del host, host_flat, host_flat_std
+
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        try:
+            extra = extra_kernels(dev)
+        except Exception as exc:          # the headline must not die on an auxiliary measurement
+            extra = {"error": repr(exc)}
+
+    if rank != 0:
+        return
+    peak, peak_src = hbm_peak()
+    alg_bytes = algorithmic_bytes(wl, n_dark)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    cpu = cpu_baseline_single(args.workload) if world == 1 and not args.no_cpu else None
+    line = {
+        "metric": "HDR merge throughput", "value": value, "unit": "Gpix*exposures/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "per_gpu_stack": f"{wl['N']}x{wl['H']}x{wl['W']}x{wl['C']}",
+                   "dark_frames": n_dark, "flat_field": bool(wl["corrections"]), "algo": args.algo,
+                   "l2": "inputs larger than L2 (no flush needed): "
+                         f"{alg_bytes / 1e9:.2f} GB streamed per step vs 126 MB L2",
+                   "parallelism": f"independent stacks x{world}, no collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "merge_staged_kernel" if args.algo != 1 else "merge_generic_kernel",
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "Gpix*exposures/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": float(tm.item()) / n_e2e, "steps": n_e2e,
+                "api": "ExposureSeries.process_HDR_image from pinned host tensors"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "extra": extra,
+    }
+    print(json.dumps(line))
+
+
+def extra_kernels(dev):
+    """Short device-resident measurements of the other three kernels (reported, not the headline)."""
+    import torch
+    import camera_linearity_b200 as cl
+    from camera_linearity_b200 import ops
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    out = {}
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    icrf_np, diff_np = icrf_tables(3)
+    icrf, diff = torch.from_numpy(icrf_np).to(dev), torch.from_numpy(diff_np).to(dev)
+    # K1: linearize one 4K RGB frame with std (25 B/sample)
+    dn = torch.randint(0, 256, (2160, 3840, 3), generator=g, device=dev, dtype=torch.uint8)
+    sd = torch.rand((2160, 3840, 3), generator=g, device=dev, dtype=torch.float64) * 0.02
+    ms = timed(lambda: ops.linearize(dn, sd, icrf, diff))
+    out["k1_linearize"] = {"ms": ms, "GB/s": dn.numel() * 25 / ms / 1e6, "shape": "2160x3840x3 u8 + f64 std"}
+    del dn, sd
+    # K3: cfg4, 600 frames 1080x1920x3
+    base = torch.randint(20, 231, (1, 1080, 1920, 3), generator=g, device=dev, dtype=torch.int16)
+    frames = torch.empty((600, 1080, 1920, 3), dtype=torch.uint8, device=dev)
+    for f0 in range(0, 600, 50):
+        noise = torch.round(torch.randn((50, 1080, 1920, 3), generator=g, device=dev) * 3).to(torch.int16)
+        frames[f0:f0 + 50] = torch.clamp(base + noise, 0, 255).to(torch.uint8)
+    del noise
+    ws = torch.empty(ops._lib.load().cl_welford_stack_workspace_bytes(600, frames[0].numel()), dtype=torch.uint8, device=dev)
+    ms = timed(lambda: ops.welford_stack(frames, None, 255.0, ws), reps=3, warm=1)
+    nb = frames.numel() + frames[0].numel() * 17
+    out["k3_welford_stack"] = {"ms": ms, "GB/s": nb / ms / 1e6, "Gpix*frames/s": 600 * 1080 * 1920 / ms / 1e6,
+                               "shape": "cfg4: 600x1080x1920x3 u8"}
+    del frames, ws
+    # K4: cfg3, S=64 candidates, 400k px x 5 exposures
+    x = np.linspace(0, 1, 256)
+    modes = np.stack([np.sin((k + 1) * np.pi * x) * x for k in range(5)], axis=1)
+    pca, _ = np.linalg.qr(modes)
+    rng = np.random.default_rng(3)
+    tt = 0.005 * 2.0 ** np.arange(5)
+    rad = rng.uniform(0, 1, (1000, 400, 1)) * 25
+    stack = np.rint(255 * np.clip(rad * tt[None, None, :], 0, 1) ** (1 / 2.2)).astype(np.uint8)
+    std = rng.uniform(0.002, 0.02, stack.shape)
+    params = rng.uniform(-0.05, 0.05, (5, 64))
+    for name, sdv in (("nostd", None), ("std", std)):
+        ev = cl.EnergyEvaluator(x ** 2.2, pca, stack, sdv, 5, 250, True, tt, 64, shard=False)
+        plan = ev.plan
+        plan.set_params(torch.from_numpy(np.ascontiguousarray(params.T)))
+
+        def one():
+            plan.curves_and_tables()
+            plan.partial()
+            plan.finalize()
+        ms = timed(one, reps=10, warm=2)
+        out[f"k4_icrf_energy_{name}"] = {"ms_per_population": ms, "evals/s": 64 / ms * 1e3,
+                                         "pair_evals/s": 64 * 400000 * 10 / ms * 1e3,
+                                         "shape": "cfg3: S=64, 400k px x 5 exposures (4.0M pixel-pairs per eval)"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 generic kernel, 2 staged kernel")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, args.workload)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,508 @@
+// K2: fused weighted HDR merge -- C ABI, generic register kernel and the stand-alone Measurand
+// kernels (Gaussian weight, bad-pixel filter, flat-field normalisation, ROI means).
+// Replaces exposure_series.py:317-397 + measurand.py:543-618 of the reference.
+//
+// Generic kernel ("algo 1"): any channel count, uint8 or uint16 DNs, std images or an STD table.
+// Each thread owns 4 consecutive samples; pass A sums the Gaussian weights over the N exposures
+// (DN bytes only), pass B re-reads the DNs (L1/L2 hits) together with the float64 std stream and
+// accumulates value and variance in float64 registers.  Weight / ICRF tables are pre-multiplied
+// ({w}, {w*g, dICRF}) and live in shared memory for 8-bit data, in an L2-resident workspace for
+// 16-bit data.  The fast path for 8-bit RGB/mono stacks is hdr_merge_staged.cu ("algo 2").
+#include "hdr_merge.cuh"
+
+#include <cstring>
+
+namespace cl {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kVec = 4;
+
+// ---- table construction -----------------------------------------------------------------------
+// wt[d] = w(d / max_dn);  pb[d*C + c] = { w * lut[d][c], dlut[d][c] }
+__global__ void build_tables_kernel(const double* __restrict__ lut, const double* __restrict__ dlut,
+                                    double max_dn, int bits, int C, double* __restrict__ wt,
+                                    double2* __restrict__ pb) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= bits) return;
+    double w, dw;
+    gaussian_weight(__ddiv_rn((double)d, max_dn), w, dw);
+    wt[d] = w;
+    for (int c = 0; c < C; ++c) pb[d * C + c] = make_double2(w * lut[d * C + c], dlut[d * C + c]);
+}
+
+template <typename DN>
+__device__ __forceinline__ void load_dn4(const DN* __restrict__ img, int64_t base, int64_t n,
+                                         uint32_t (&d)[kVec]) {
+    if (base + kVec <= n) {
+        if (sizeof(DN) == 1) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(img + base);
+            d[0] = u & 0xFF; d[1] = (u >> 8) & 0xFF; d[2] = (u >> 16) & 0xFF; d[3] = u >> 24;
+        } else {
+            const uint2 u = *reinterpret_cast<const uint2*>(img + base);
+            d[0] = u.x & 0xFFFF; d[1] = u.x >> 16; d[2] = u.y & 0xFFFF; d[3] = u.y >> 16;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) d[j] = (base + j < n) ? (uint32_t)img[base + j] : 0u;
+    }
+}
+
+__device__ __forceinline__ void load_f64x4(const double* __restrict__ a, int64_t base, int64_t n,
+                                           double (&v)[kVec]) {
+    if (base + kVec <= n) {
+        const double2 lo = *reinterpret_cast<const double2*>(a + base);
+        const double2 hi = *reinterpret_cast<const double2*>(a + base + 2);
+        v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) v[j] = (base + j < n) ? a[base + j] : 0.0;
+    }
+}
+
+template <typename DN, bool TAB_SMEM>
+__global__ void __launch_bounds__(kThreads)
+merge_generic_kernel(const __grid_constant__ MergeParams p, const int64_t first_item) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int C = p.C;
+    const double* wt;
+    const double2* pb;
+    const double* stdlut = p.std_lut;
+    if (TAB_SMEM) {
+        double* s_wt = reinterpret_cast<double*>(smem_raw);
+        double2* s_pb = reinterpret_cast<double2*>(s_wt + p.bits);
+        double* s_sl = reinterpret_cast<double*>(s_pb + p.bits * C);
+        for (int d = threadIdx.x; d < p.bits; d += blockDim.x) {
+            double w, dw;
+            gaussian_weight(__ddiv_rn((double)d, p.max_dn), w, dw);
+            s_wt[d] = w;
+            for (int c = 0; c < C; ++c) {
+                s_pb[d * C + c] = make_double2(w * p.lut[d * C + c], p.dlut[d * C + c]);
+                if (p.std_lut) s_sl[d * C + c] = p.std_lut[d * C + c];
+            }
+        }
+        __syncthreads();
+        wt = s_wt;
+        pb = s_pb;
+        if (p.std_lut) stdlut = s_sl;
+    } else {
+        wt = p.g_wt;
+        pb = p.g_pb;
+    }
+
+    const int64_t n = (int64_t)p.H * p.W * C;
+    const int64_t n_items = (n + kVec - 1) / kVec;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t row = (int64_t)p.W * C;
+    for (int64_t it = first_item + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items;
+         it += stride) {
+        const int64_t base = it * kVec;
+        int cidx[kVec];
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) cidx[j] = (int)((base + j) % C);
+
+        // ---- pass A: sum of weights (exposure_series.py:328-343) ----
+        double S[kVec] = {0.0, 0.0, 0.0, 0.0};
+        uint32_t hot_any = 0;  // bit k set: this item has a bad pixel in exposure k
+        for (int k = 0; k < p.n; ++k) {
+            uint32_t d[kVec];
+            load_dn4(reinterpret_cast<const DN*>(p.dn[k]), base, n, d);
+            if (p.dark[k]) {
+                uint32_t dk[kVec];
+                load_dn4(reinterpret_cast<const DN*>(p.dark[k]), base, n, dk);
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    if (dk[j] >= p.hot_dn[k] && base + j < n) {
+                        const int64_t i = base + j;
+                        const int y = (int)(i / row);
+                        const int x = (int)((i - (int64_t)y * row) / C);
+                        d[j] = median_dn(reinterpret_cast<const DN*>(p.dn[k]), y, x, cidx[j], p.H,
+                                         p.W, C, p.K);
+                        hot_any |= 1u << k;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kVec; ++j) S[j] += wt[d[j]];
+        }
+        double rS[kVec];
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) rS[j] = 1.0 / S[j];
+
+        // ---- pass B: weighted radiance and variance (exposure_series.py:372-394) ----
+        double av[kVec] = {0.0, 0.0, 0.0, 0.0}, as[kVec] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < p.n; ++k) {
+            const DN* img = reinterpret_cast<const DN*>(p.dn[k]);
+            uint32_t d[kVec];
+            load_dn4(img, base, n, d);
+            double sg[kVec];
+            if (p.std[k]) {
+                load_f64x4(p.std[k], base, n, sg);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) sg[j] = stdlut[(int64_t)d[j] * C + cidx[j]];
+            }
+            if (hot_any & (1u << k)) {
+                uint32_t dk[kVec];
+                load_dn4(reinterpret_cast<const DN*>(p.dark[k]), base, n, dk);
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    if (dk[j] >= p.hot_dn[k] && base + j < n) {
+                        const int64_t i = base + j;
+                        const int y = (int)(i / row);
+                        const int x = (int)((i - (int64_t)y * row) / C);
+                        d[j] = median_dn(img, y, x, cidx[j], p.H, p.W, C, p.K);
+                        sg[j] = median_std(p.std[k], img, p.std_lut, y, x, cidx[j], p.H, p.W, C, p.K);
+                    }
+                }
+            }
+            const double rt = p.inv_t[k];
+#pragma unroll
+            for (int j = 0; j < kVec; ++j) {
+                const double2 e = pb[(int64_t)d[j] * C + cidx[j]];
+                merge_accumulate(wt[d[j]], e.x, e.y, kappa_of(d[j], p.kappa_scale), sg[j], rS[j], rt,
+                                 av[j], as[j]);
+            }
+        }
+
+        double ov[kVec], os[kVec];
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) {
+            ov[j] = av[j] * rS[j];
+            os[j] = sqrt(as[j]) * rS[j];
+        }
+        if (p.flat_bytes) {
+#pragma unroll
+            for (int j = 0; j < kVec; ++j) {
+                if (base + j < n) {
+                    const double fv = flat_value(p.flat, p.flat_bytes, base + j, p.max_dn);
+                    flat_epilogue(ov[j], os[j], fv, p.flat_std[base + j], p.flat_means[cidx[j]],
+                                  p.flat_means[C + cidx[j]]);
+                }
+            }
+        }
+        if (base + kVec <= n) {
+            *reinterpret_cast<double2*>(p.out_val + base) = make_double2(ov[0], ov[1]);
+            *reinterpret_cast<double2*>(p.out_val + base + 2) = make_double2(ov[2], ov[3]);
+            *reinterpret_cast<double2*>(p.out_std + base) = make_double2(os[0], os[1]);
+            *reinterpret_cast<double2*>(p.out_std + base + 2) = make_double2(os[2], os[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kVec; ++j)
+                if (base + j < n) {
+                    p.out_val[base + j] = ov[j];
+                    p.out_std[base + j] = os[j];
+                }
+        }
+    }
+}
+
+template <typename DN>
+int launch_generic(const MergeParams& p, bool tab_smem, int64_t first_item, cudaStream_t stream) {
+    const int64_t n = (int64_t)p.H * p.W * p.C;
+    const int64_t n_items = (n + kVec - 1) / kVec - first_item;
+    if (n_items <= 0) return CL_OK;
+    int64_t blocks = (n_items + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * 6;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (tab_smem) {
+        const size_t smem = (size_t)p.bits * 8 + (size_t)p.bits * p.C * 16 +
+                            (p.std_lut ? (size_t)p.bits * p.C * 8 : 0);
+        auto k = merge_generic_kernel<DN, true>;
+        if (smem > 48 * 1024) {
+            cudaError_t e =
+                cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_status(e);
+        }
+        k<<<(unsigned)blocks, kThreads, smem, stream>>>(p, first_item);
+    } else {
+        merge_generic_kernel<DN, false><<<(unsigned)blocks, kThreads, 0, stream>>>(p, first_item);
+    }
+    return launched();
+}
+
+// ---- ROI means ------------------------------------------------------------------------------------
+constexpr int kRoiThreads = 256;
+
+__global__ void roi_partial_kernel(const void* __restrict__ flat, int flat_bytes, double max_dn,
+                                   const double* __restrict__ flat_std, int W, int C, int r0, int c0,
+                                   int rh, int rw, double* __restrict__ partial) {
+    // block b reduces ROI pixels [b*chunk, (b+1)*chunk) for every channel, fixed order
+    __shared__ double red[kRoiThreads / 32][2 * CL_MAX_CHANNELS];
+    const int64_t npx = (int64_t)rh * rw;
+    const int64_t chunk = (npx + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * chunk;
+    const int64_t hi = lo + chunk < npx ? lo + chunk : npx;
+    double acc[2 * CL_MAX_CHANNELS];
+    for (int c = 0; c < 2 * C; ++c) acc[c] = 0.0;
+    for (int64_t q = lo + threadIdx.x; q < hi; q += blockDim.x) {
+        const int y = r0 + (int)(q / rw), x = c0 + (int)(q % rw);
+        const int64_t i = ((int64_t)y * W + x) * C;
+        for (int c = 0; c < C; ++c) {
+            acc[c] += flat_value(flat, flat_bytes, i + c, max_dn);
+            acc[C + c] += flat_std[i + c];
+        }
+    }
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    for (int c = 0; c < 2 * C; ++c) {
+        const double v = warp_sum(acc[c]);
+        if (lane == 0) red[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * C) {
+        double s = 0.0;
+        for (int w = 0; w < kRoiThreads / 32; ++w) s += red[w][threadIdx.x];
+        partial[(int64_t)blockIdx.x * 2 * C + threadIdx.x] = s;
+    }
+}
+
+__global__ void roi_final_kernel(const double* __restrict__ partial, int n_blocks, int C,
+                                 double count, double* __restrict__ out) {
+    const int c = threadIdx.x;
+    if (c >= 2 * C) return;
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)b * 2 * C + c];
+    out[c] = s / count;
+}
+
+constexpr int kRoiBlocks = 64;
+
+// ---- stand-alone Measurand kernels ------------------------------------------------------------------
+__global__ void gaussian_weight_kernel(const double* __restrict__ val, double* __restrict__ w,
+                                       double* __restrict__ dw, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double a, b;
+        gaussian_weight(val[i], a, b);
+        w[i] = a;
+        if (dw) dw[i] = b;
+    }
+}
+
+__global__ void bad_pixel_filter_kernel(const double* __restrict__ val, const double* __restrict__ std,
+                                        const double* __restrict__ dark, double thr, int K, int H,
+                                        int W, int C, double* __restrict__ out_val,
+                                        double* __restrict__ out_std) {
+    const int64_t n = (int64_t)H * W * C;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t row = (int64_t)W * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double v = val[i];
+        double s = std ? std[i] : 0.0;
+        if (dark[i] > thr) {
+            const int y = (int)(i / row);
+            const int x = (int)((i - (int64_t)y * row) / C);
+            const int c = (int)(i % C);
+            double win[CL_MAX_MEDIAN_KERNEL * CL_MAX_MEDIAN_KERNEL];
+            const int lo = K / 2;
+            for (int pass = 0; pass < (std ? 2 : 1); ++pass) {
+                const double* src = pass ? std : val;
+                int m = 0;
+                for (int dy = -lo; dy < K - lo; ++dy) {
+                    const int yy = reflect_index(y + dy, H);
+                    for (int dx = -lo; dx < K - lo; ++dx)
+                        win[m++] = src[((int64_t)yy * W + reflect_index(x + dx, W)) * C + c];
+                }
+                const double med = select_rank(win, m, (K * K) / 2);
+                if (pass) s = med; else v = med;
+            }
+        }
+        out_val[i] = v;
+        if (std) out_std[i] = s;
+    }
+}
+
+__global__ void flat_normalize_kernel(const double* __restrict__ val, const double* __restrict__ std,
+                                      const double* __restrict__ fv, const double* __restrict__ fs,
+                                      const double* __restrict__ means, int64_t n, int C,
+                                      double* __restrict__ out_val, double* __restrict__ out_std) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c = (int)(i % C);
+        double v = val[i], s = std[i];
+        flat_epilogue(v, s, fv[i], fs[i], means[c], means[C + c]);
+        out_val[i] = v;
+        out_std[i] = s;
+    }
+}
+
+inline unsigned grid_for(int64_t n, int threads) {
+    int64_t b = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (b > cap) b = cap;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+size_t table_bytes(int bits, int C) { return (size_t)bits * 8 + (size_t)bits * C * 16; }
+
+}  // namespace
+
+int launch_merge_generic_range(const MergeParams& p, int64_t first_item, cudaStream_t stream) {
+    return launch_generic<uint8_t>(p, true, first_item, stream);
+}
+
+}  // namespace cl
+
+extern "C" {
+
+size_t cl_hdr_merge_workspace_bytes(const cl_hdr_merge_args* a) {
+    if (!a) return 0;
+    if (a->bits > 256) return cl::table_bytes(a->bits, a->channels);
+    return 0;
+}
+
+int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace cl;
+    CL_REQUIRE(a != nullptr);
+    CL_REQUIRE(a->n_exposures >= 1 && a->n_exposures <= CL_MAX_EXPOSURES);
+    CL_REQUIRE(a->height >= 0 && a->width >= 0 && a->channels >= 1 && a->channels <= CL_MAX_CHANNELS);
+    CL_REQUIRE(a->dn_bytes == 1 || a->dn_bytes == 2);
+    CL_REQUIRE((a->dn_bytes == 1 && a->bits >= 256) || (a->dn_bytes == 2 && a->bits >= 65536));
+    CL_REQUIRE(a->bits <= 65536);
+    CL_REQUIRE(a->dn && a->exposure_s && a->lut && a->dlut && a->out_val && a->out_std);
+    CL_REQUIRE(a->median_kernel >= 1 && a->median_kernel <= CL_MAX_MEDIAN_KERNEL);
+    CL_REQUIRE(a->flat_bytes == 0 || a->flat_bytes == 1 || a->flat_bytes == 2 || a->flat_bytes == 8);
+    if (a->flat_bytes) CL_REQUIRE(a->flat && a->flat_std && a->flat_means);
+    if ((int64_t)a->height * a->width == 0) return CL_OK;
+    if ((int64_t)a->height * a->width * a->channels > (int64_t)1 << 40) return CL_ERR_UNSUPPORTED;
+
+    MergeParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.n = a->n_exposures; p.H = a->height; p.W = a->width; p.C = a->channels; p.bits = a->bits;
+    p.K = a->median_kernel;
+    p.max_dn = a->dn_bytes == 1 ? 255.0 : 65535.0;
+    p.kappa_scale = -60.0 / p.max_dn;
+    p.lut = a->lut; p.dlut = a->dlut; p.std_lut = a->std_lut;
+    p.flat = a->flat; p.flat_std = a->flat_std; p.flat_means = a->flat_means;
+    p.flat_bytes = a->flat_bytes;
+    p.out_val = a->out_val; p.out_std = a->out_std;
+    if (!aligned(p.out_val, 16) || !aligned(p.out_std, 16)) return CL_ERR_ALIGNMENT;
+    bool all_std = true;
+    for (int k = 0; k < p.n; ++k) {
+        CL_REQUIRE(a->dn[k] != nullptr);
+        p.dn[k] = a->dn[k];
+        p.std[k] = a->std ? a->std[k] : nullptr;
+        if (!p.std[k]) {
+            all_std = false;
+            CL_REQUIRE(a->std_lut != nullptr);
+        }
+        if (!aligned(p.dn[k], 16) || (p.std[k] && !aligned(p.std[k], 16))) return CL_ERR_ALIGNMENT;
+        const double t = a->exposure_s[k];
+        CL_REQUIRE(t == t && t != 0.0);
+        p.inv_t[k] = 1.0 / t;
+        p.dark[k] = a->dark ? a->dark[k] : nullptr;
+        p.hot_dn[k] = 0xFFFFFFFFu;
+        if (p.dark[k]) {
+            if (!aligned(p.dark[k], 16)) return CL_ERR_ALIGNMENT;
+            const double scale = a->dark_scale ? a->dark_scale[k] : 1.0;
+            CL_REQUIRE(scale > 0.0);
+            // mask = (dark_dn / MAX_DN) [* scale] > threshold  (image_set.py:223,260;
+            // measurand.py:545) evaluated in IEEE double exactly as NumPy does; it is monotone
+            // in dark_dn, so it reduces to an integer comparison on the device.
+            const uint32_t top = (uint32_t)p.max_dn;
+            for (uint32_t d = 0; d <= top; ++d) {
+                volatile double v = (double)d / p.max_dn;
+                if (scale != 1.0) v = v * scale;
+                if (v > a->dark_threshold) { p.hot_dn[k] = d; break; }
+            }
+            p.any_dark = 1;
+        }
+    }
+
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool tab_smem = a->bits <= 256;
+    if (!tab_smem) {
+        const size_t need = table_bytes(p.bits, p.C);
+        if (!workspace || workspace_bytes < need) return CL_ERR_WORKSPACE;
+        if (!aligned(workspace, 16)) return CL_ERR_ALIGNMENT;
+        double* wt = reinterpret_cast<double*>(workspace);
+        double2* pb = reinterpret_cast<double2*>(wt + p.bits);
+        build_tables_kernel<<<(p.bits + 255) / 256, 256, 0, s>>>(p.lut, p.dlut, p.max_dn, p.bits, p.C,
+                                                                wt, pb);
+        int st = launched();
+        if (st != CL_OK) return st;
+        p.g_wt = wt;
+        p.g_pb = pb;
+    }
+
+    int algo = a->algo;
+    const bool staged_ok = merge_staged_supported(p, all_std);
+    if (algo == 0) algo = staged_ok ? 2 : 1;
+    if (algo == 2) {
+        if (!staged_ok) return CL_ERR_UNSUPPORTED;
+        return launch_merge_staged(p, s);
+    }
+    if (algo != 1) return CL_ERR_INVALID_ARGUMENT;
+    if (a->dn_bytes == 1) return launch_generic<uint8_t>(p, tab_smem, 0, s);
+    return launch_generic<uint16_t>(p, tab_smem, 0, s);
+}
+
+size_t cl_flat_roi_means_workspace_bytes(int height, int width, int channels) {
+    (void)height; (void)width;
+    return (size_t)cl::kRoiBlocks * 2 * (channels > 0 ? channels : 1) * sizeof(double);
+}
+
+int cl_flat_roi_means(const void* flat, int flat_bytes, double max_dn, const double* flat_std,
+                      int height, int width, int channels, int r0, int r1, int c0, int c1,
+                      double* out_means, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace cl;
+    CL_REQUIRE(flat && flat_std && out_means);
+    CL_REQUIRE(flat_bytes == 1 || flat_bytes == 2 || flat_bytes == 8);
+    CL_REQUIRE(height > 0 && width > 0 && channels >= 1 && channels <= CL_MAX_CHANNELS);
+    if (!workspace || workspace_bytes < cl_flat_roi_means_workspace_bytes(height, width, channels))
+        return CL_ERR_WORKSPACE;
+    // NumPy slice clamping (negative bounds are not produced by the reference formula)
+    CL_REQUIRE(r0 >= 0 && c0 >= 0);
+    if (r1 > height) r1 = height;
+    if (c1 > width) c1 = width;
+    const int rh = r1 > r0 ? r1 - r0 : 0, rw = c1 > c0 ? c1 - c0 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    double* partial = reinterpret_cast<double*>(workspace);
+    // an empty ROI yields 0/0 = NaN, like np.mean of an empty slice
+    roi_partial_kernel<<<kRoiBlocks, kRoiThreads, 0, s>>>(flat, flat_bytes, max_dn, flat_std, width,
+                                                         channels, r0, c0, rw > 0 ? rh : 0,
+                                                         rw > 0 ? rw : 1, partial);
+    int st = launched();
+    if (st != CL_OK) return st;
+    roi_final_kernel<<<1, 32, 0, s>>>(partial, kRoiBlocks, channels, (double)rh * (double)rw,
+                                      out_means);
+    return launched();
+}
+
+int cl_gaussian_weight(const double* val, double* w, double* dw, int64_t n, void* stream) {
+    using namespace cl;
+    CL_REQUIRE(n >= 0);
+    if (n == 0) return CL_OK;
+    CL_REQUIRE(val && w);
+    gaussian_weight_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(val, w, dw, n);
+    return launched();
+}
+
+int cl_bad_pixel_filter(const double* val, const double* std, const double* dark_val,
+                        double threshold, int kernel, int height, int width, int channels,
+                        double* out_val, double* out_std, void* stream) {
+    using namespace cl;
+    CL_REQUIRE(height >= 0 && width >= 0 && channels >= 1);
+    CL_REQUIRE(kernel >= 1 && kernel <= CL_MAX_MEDIAN_KERNEL);
+    const int64_t n = (int64_t)height * width * channels;
+    if (n == 0) return CL_OK;
+    CL_REQUIRE(val && dark_val && out_val && (!std || out_std));
+    bad_pixel_filter_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        val, std, dark_val, threshold, kernel, height, width, channels, out_val, out_std);
+    return launched();
+}
+
+int cl_flat_field_normalize(const double* val, const double* std, const double* flat_val,
+                            const double* flat_std, const double* flat_means, int64_t n, int channels,
+                            double* out_val, double* out_std, void* stream) {
+    using namespace cl;
+    CL_REQUIRE(n >= 0 && channels >= 1 && channels <= CL_MAX_CHANNELS);
+    if (n == 0) return CL_OK;
+    CL_REQUIRE(val && std && flat_val && flat_std && flat_means && out_val && out_std);
+    flat_normalize_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        val, std, flat_val, flat_std, flat_means, n, channels, out_val, out_std);
+    return launched();
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// K2 shared definitions: kernel parameter block, per-exposure accumulation, median replace and
+// the flat-field epilogue, used by both HDR-merge kernels (generic register kernel and the
+// bulk-copy staged kernel).  The two kernels run the same arithmetic in the same order, so their
+// outputs are bit-identical (tests/test_gpu_hdr_merge.py checks that).
+#pragma once
+
+#include "common.cuh"
+
+namespace cl {
+
+struct MergeParams {
+    const void* dn[CL_MAX_EXPOSURES];
+    const double* std[CL_MAX_EXPOSURES];
+    const void* dark[CL_MAX_EXPOSURES];
+    double inv_t[CL_MAX_EXPOSURES];          // 1 / exposure time
+    uint32_t hot_dn[CL_MAX_EXPOSURES];       // smallest dark DN counted as a bad pixel
+    int32_t n, H, W, C, bits, K;
+    double max_dn;
+    double kappa_scale;                      // -60 / max_dn : dw/w = kappa_scale*dn + 30
+    const double* lut;
+    const double* dlut;
+    const double* std_lut;
+    const void* flat;
+    const double* flat_std;
+    const double* flat_means;
+    int32_t flat_bytes;
+    int32_t any_dark;
+    double* out_val;
+    double* out_std;
+    // tables in global memory (16-bit path): wt[bits], pb[bits][C] = {w*g, dlut}
+    const double* g_wt;
+    const double2* g_pb;
+};
+
+// One exposure's contribution for one sample.  With S = sum of weights and rS = 1/S:
+//   val = rS * sum_k (w g) / t_k                                   exposure_series.py:388
+//   std = rS * sqrt( sum_k ( (dw g + w dg - dw w g rS) dg / t_k )^2 )              :389,394
+// where P1 = w*g and dgl = dlut[dn] come from the tables, dw = kappa*w, dg = dgl*sigma.
+__device__ __forceinline__ void merge_accumulate(double w, double p1, double dgl, double kappa,
+                                                 double sigma, double rS, double rt, double& acc_val,
+                                                 double& acc_var) {
+    const double a = kappa * p1;        // dw * g
+    const double b = w * dgl;           // w * dICRF
+    const double e = a * w;             // dw * w * g
+    const double x = fma(b, sigma, a);  // dw*g + w*dg
+    const double z = fma(-e, rS, x);
+    const double y = (dgl * sigma) * rt;
+    const double q = z * y;
+    acc_var = fma(q, q, acc_var);
+    acc_val = fma(p1, rt, acc_val);
+}
+
+__device__ __forceinline__ double kappa_of(uint32_t d, double kappa_scale) {
+    return fma(u32_to_double(d), kappa_scale, 30.0);
+}
+
+template <typename DN>
+__device__ __noinline__ uint32_t median_dn(const DN* __restrict__ img, int y, int x, int c, int H,
+                                              int W, int C, int K) {
+    uint32_t win[CL_MAX_MEDIAN_KERNEL * CL_MAX_MEDIAN_KERNEL];
+    const int lo = K / 2;
+    int m = 0;
+    for (int dy = -lo; dy < K - lo; ++dy) {
+        const int yy = reflect_index(y + dy, H);
+        for (int dx = -lo; dx < K - lo; ++dx) {
+            const int xx = reflect_index(x + dx, W);
+            win[m++] = (uint32_t)img[((int64_t)yy * W + xx) * C + c];
+        }
+    }
+    return select_rank(win, m, (K * K) / 2);
+}
+
+// Median of the uncertainty image; when there is no image the uncertainty of a neighbour is the
+// STD-table value of ITS (unfiltered) DN (image_set.py:228-243, 365-385).
+template <typename DN>
+__device__ __noinline__ double median_std(const double* __restrict__ std_img,
+                                             const DN* __restrict__ dn_img,
+                                             const double* __restrict__ std_lut, int y, int x, int c,
+                                             int H, int W, int C, int K) {
+    double win[CL_MAX_MEDIAN_KERNEL * CL_MAX_MEDIAN_KERNEL];
+    const int lo = K / 2;
+    int m = 0;
+    for (int dy = -lo; dy < K - lo; ++dy) {
+        const int yy = reflect_index(y + dy, H);
+        for (int dx = -lo; dx < K - lo; ++dx) {
+            const int xx = reflect_index(x + dx, W);
+            const int64_t j = ((int64_t)yy * W + xx) * C + c;
+            win[m++] = std_img ? std_img[j] : std_lut[(int64_t)dn_img[j] * C + c];
+        }
+    }
+    return select_rank(win, m, (K * K) / 2);
+}
+
+// normalize_by_map, measurand.py:586-602 (operand order kept; true divisions, once per sample).
+__device__ __forceinline__ void flat_epilogue(double& val, double& sd, double fv, double fs, double m,
+                                              double ms) {
+    const double fv2 = fv * fv;
+    const double m2 = m * m;
+    const double v2 = val * val;
+    const double u_acq = ((sd * sd) / fv2) * m2;
+    const double u_ff = ((v2 / (fv2 * fv2)) * (fs * fs)) * m2;
+    const double u_ffm = (v2 / fv2) * (ms * ms);
+    sd = sqrt(u_acq + u_ff + u_ffm);
+    val = (val / fv) * m;
+}
+
+__device__ __forceinline__ double flat_value(const void* flat, int flat_bytes, int64_t i,
+                                             double max_dn) {
+    if (flat_bytes == 8) return reinterpret_cast<const double*>(flat)[i];
+    if (flat_bytes == 2) return __ddiv_rn((double)reinterpret_cast<const uint16_t*>(flat)[i], max_dn);
+    return __ddiv_rn((double)reinterpret_cast<const uint8_t*>(flat)[i], max_dn);
+}
+
+int launch_merge_staged(const MergeParams& p, cudaStream_t stream);   // hdr_merge_staged.cu
+bool merge_staged_supported(const MergeParams& p, bool all_std_images);
+
+}  // namespace cl

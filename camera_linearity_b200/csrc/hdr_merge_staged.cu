@@ -1,0 +1,306 @@
+// K2 fast path ("algo 2"): bulk-copy staged HDR merge for 8-bit, 3-channel stacks on sm_100a.
+//
+// One persistent CTA per SM (grid = #SMs), 16 consumer warps + 2 producer warps:
+//   * producer warp 0 streams the float64 uncertainty images through a ring of shared-memory
+//     stages with cp.async.bulk (the TMA engine's 1-D bulk copy, SASS UBLKCP) and mbarrier
+//     transaction counts -- one 12 KB chunk per (tile, exposure);
+//   * producer warp 1 bulk-copies the DN (and dark-frame) bytes of ALL exposures of the next
+//     tile into the "A buffer" while the consumers are still in pass B of the current tile;
+//   * consumer thread t owns pixel t of the 512-pixel tile (3 interleaved samples).  Pass A sums
+//     the Gaussian weights from the A buffer and packs the (median-repaired) DNs into one
+//     register per exposure; pass B consumes one ring stage per exposure.
+// Shared-memory tables are replicated per lane so that the random, DN-indexed gathers are bank-
+// conflict free: w[dn] as 16 copies of a double (LDS.64: half-warp lanes hit 16 distinct bank
+// pairs), {w*g, dICRF}[c][dn] as 8 copies of a double2 (LDS.128: quarter-warp lanes hit 8
+// distinct bank quads).  Without the replication a random 8-bit gather costs ~3 wavefronts per
+// half-warp and the kernel is shared-memory bound well below the HBM roofline.
+// Every input byte crosses HBM once: 9 B per sample-exposure (+1 with a dark frame), 16 B out.
+#include "hdr_merge.cuh"
+
+namespace cl {
+namespace {
+
+constexpr int kTilePx = 512;
+constexpr int kC = 3;
+constexpr int kConsumerWarps = kTilePx / 32;
+constexpr int kThreads = kTilePx + 64;          // + ring producer warp + A-buffer producer warp
+constexpr int kDnChunk = kTilePx * kC;          // bytes of one exposure's DN tile
+constexpr int kStdChunk = kTilePx * kC * 8;     // bytes of one exposure's std tile
+constexpr int kLutACopies = 16;
+constexpr int kLutBCopies = 8;
+constexpr int kMaxStages = 8;
+constexpr size_t kSmemLimit = 227 * 1024;
+
+struct StagedLayout {
+    int stages;
+    uint32_t off_lutA, off_lutB, off_abuf_dn, off_abuf_dark, off_ring, off_bars, total;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(kThreads, 1)
+merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L, const int n_tiles) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* lutA = reinterpret_cast<double*>(smem + L.off_lutA);
+    double2* lutB = reinterpret_cast<double2*>(smem + L.off_lutB);
+    uint8_t* abuf_dn = smem + L.off_abuf_dn;
+    uint8_t* abuf_dark = smem + L.off_abuf_dark;
+    unsigned char* ring = smem + L.off_ring;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
+    uint64_t* full = bars;                    // [stages]  producer -> consumers (tx bytes)
+    uint64_t* empty = bars + kMaxStages;      // [stages]  consumers -> producer
+    uint64_t* a_full = bars + 2 * kMaxStages;
+    uint64_t* a_empty = a_full + 1;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int stages = L.stages;
+    const bool has_flat = p.flat_bytes != 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, kConsumerWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // replicated tables (see file header)
+    for (int d = tid; d < 256; d += kThreads) {
+        double w, dw;
+        gaussian_weight(__ddiv_rn((double)d, p.max_dn), w, dw);
+#pragma unroll
+        for (int r = 0; r < kLutACopies; ++r) lutA[d * kLutACopies + r] = w;
+        for (int c = 0; c < kC; ++c) {
+            const double2 e = make_double2(w * p.lut[d * kC + c], p.dlut[d * kC + c]);
+#pragma unroll
+            for (int r = 0; r < kLutBCopies; ++r) lutB[(c * 256 + d) * kLutBCopies + r] = e;
+        }
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ===== ring producer: std chunks (tile-major, exposure-minor; flat std last) =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const size_t off = (size_t)tile * kTilePx * kC;   // first sample of the tile
+                const int chunks = p.n + (has_flat ? 1 : 0);
+                for (int k = 0; k < chunks; ++k, ++it) {
+                    const int s = it % stages;
+                    mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], kStdChunk);
+                    const double* src = (k < p.n ? p.std[k] : p.flat_std) + off;
+                    bulk_g2s(ring + (size_t)s * kStdChunk, src, kStdChunk, &full[s]);
+                }
+            }
+        }
+    } else if (warp == kConsumerWarps + 1) {
+        // ===== A-buffer producer: DN (+ dark) bytes of every exposure of one tile =====
+        if (lane == 0) {
+            uint32_t ti = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+                const size_t off = (size_t)tile * kDnChunk;
+                mbar_wait(a_empty, (ti & 1) ^ 1);
+                uint32_t bytes = 0;
+                for (int k = 0; k < p.n; ++k) bytes += kDnChunk + (p.dark[k] ? kDnChunk : 0);
+                mbar_expect_tx(a_full, bytes);
+                for (int k = 0; k < p.n; ++k) {
+                    bulk_g2s(abuf_dn + k * kDnChunk, reinterpret_cast<const uint8_t*>(p.dn[k]) + off,
+                             kDnChunk, a_full);
+                    if (p.dark[k])
+                        bulk_g2s(abuf_dark + k * kDnChunk,
+                                 reinterpret_cast<const uint8_t*>(p.dark[k]) + off, kDnChunk, a_full);
+                }
+            }
+        }
+    } else {
+        // ===== consumers: thread tid owns pixel tid of each tile =====
+        const double* myA = lutA + (lane & (kLutACopies - 1));
+        const double2* myB = lutB + (lane & (kLutBCopies - 1));
+        uint32_t it = 0, ti = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+            const int64_t px = (int64_t)tile * kTilePx + tid;
+            const int y = (int)(px / p.W), x = (int)(px - (int64_t)y * p.W);
+
+            // ---- pass A: sum of weights; pack DNs + bad-pixel flags into registers ----
+            mbar_wait(a_full, ti & 1);
+            uint32_t pk[NMAX];
+            double S0 = 0.0, S1 = 0.0, S2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < NMAX; ++k) {
+                if (k < p.n) {
+                    const uint8_t* a = abuf_dn + k * kDnChunk + tid * kC;
+                    uint32_t d0 = a[0], d1 = a[1], d2 = a[2], hot = 0;
+                    if (p.dark[k]) {
+                        const uint8_t* b = abuf_dark + k * kDnChunk + tid * kC;
+                        const uint8_t* img = reinterpret_cast<const uint8_t*>(p.dn[k]);
+                        if (b[0] >= p.hot_dn[k]) { hot |= 1; d0 = median_dn(img, y, x, 0, p.H, p.W, kC, p.K); }
+                        if (b[1] >= p.hot_dn[k]) { hot |= 2; d1 = median_dn(img, y, x, 1, p.H, p.W, kC, p.K); }
+                        if (b[2] >= p.hot_dn[k]) { hot |= 4; d2 = median_dn(img, y, x, 2, p.H, p.W, kC, p.K); }
+                    }
+                    S0 += myA[d0 * kLutACopies];
+                    S1 += myA[d1 * kLutACopies];
+                    S2 += myA[d2 * kLutACopies];
+                    pk[k] = d0 | (d1 << 8) | (d2 << 16) | (hot << 24);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_empty);
+            const double r0 = 1.0 / S0, r1 = 1.0 / S1, r2 = 1.0 / S2;
+
+            // ---- pass B: one ring stage per exposure ----
+            double av0 = 0.0, av1 = 0.0, av2 = 0.0, as0 = 0.0, as1 = 0.0, as2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < NMAX; ++k) {
+                if (k < p.n) {
+                    const int s = it % stages;
+                    mbar_wait(&full[s], (it / stages) & 1);
+                    const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
+                    double g0 = sp[0], g1 = sp[1], g2 = sp[2];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                    ++it;
+                    const uint32_t q = pk[k];
+                    const uint32_t d0 = q & 0xFF, d1 = (q >> 8) & 0xFF, d2 = (q >> 16) & 0xFF;
+                    if (q >> 24) {
+                        const uint8_t* img = reinterpret_cast<const uint8_t*>(p.dn[k]);
+                        if (q & (1u << 24)) g0 = median_std(p.std[k], img, p.std_lut, y, x, 0, p.H, p.W, kC, p.K);
+                        if (q & (2u << 24)) g1 = median_std(p.std[k], img, p.std_lut, y, x, 1, p.H, p.W, kC, p.K);
+                        if (q & (4u << 24)) g2 = median_std(p.std[k], img, p.std_lut, y, x, 2, p.H, p.W, kC, p.K);
+                    }
+                    const double rt = p.inv_t[k];
+                    const double w0 = myA[d0 * kLutACopies], w1 = myA[d1 * kLutACopies], w2 = myA[d2 * kLutACopies];
+                    const double2 e0 = myB[(0 * 256 + d0) * kLutBCopies];
+                    const double2 e1 = myB[(1 * 256 + d1) * kLutBCopies];
+                    const double2 e2 = myB[(2 * 256 + d2) * kLutBCopies];
+                    merge_accumulate(w0, e0.x, e0.y, kappa_of(d0, p.kappa_scale), g0, r0, rt, av0, as0);
+                    merge_accumulate(w1, e1.x, e1.y, kappa_of(d1, p.kappa_scale), g1, r1, rt, av1, as1);
+                    merge_accumulate(w2, e2.x, e2.y, kappa_of(d2, p.kappa_scale), g2, r2, rt, av2, as2);
+                }
+            }
+
+            double v0 = av0 * r0, v1 = av1 * r1, v2 = av2 * r2;
+            double u0 = sqrt(as0) * r0, u1 = sqrt(as1) * r1, u2 = sqrt(as2) * r2;
+            const int64_t i0 = px * kC;
+            if (has_flat) {
+                const int s = it % stages;
+                mbar_wait(&full[s], (it / stages) & 1);
+                const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
+                const double f0 = sp[0], f1 = sp[1], f2 = sp[2];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                ++it;
+                flat_epilogue(v0, u0, flat_value(p.flat, p.flat_bytes, i0 + 0, p.max_dn), f0,
+                              p.flat_means[0], p.flat_means[kC + 0]);
+                flat_epilogue(v1, u1, flat_value(p.flat, p.flat_bytes, i0 + 1, p.max_dn), f1,
+                              p.flat_means[1], p.flat_means[kC + 1]);
+                flat_epilogue(v2, u2, flat_value(p.flat, p.flat_bytes, i0 + 2, p.max_dn), f2,
+                              p.flat_means[2], p.flat_means[kC + 2]);
+            }
+            p.out_val[i0 + 0] = v0; p.out_val[i0 + 1] = v1; p.out_val[i0 + 2] = v2;
+            p.out_std[i0 + 0] = u0; p.out_std[i0 + 1] = u1; p.out_std[i0 + 2] = u2;
+        }
+    }
+}
+
+bool make_layout(const MergeParams& p, StagedLayout& L) {
+    uint32_t off = 0;
+    L.off_lutA = off; off += 256 * kLutACopies * 8;
+    L.off_lutB = off; off += kC * 256 * kLutBCopies * 16;
+    L.off_abuf_dn = off; off += (uint32_t)p.n * kDnChunk;
+    L.off_abuf_dark = off; if (p.any_dark) off += (uint32_t)p.n * kDnChunk;
+    off = (off + 127) & ~127u;
+    L.off_ring = off;
+    const size_t room = kSmemLimit - 256 - off;
+    int stages = (int)(room / kStdChunk);
+    if (stages > kMaxStages) stages = kMaxStages;
+    L.stages = stages;
+    off += (uint32_t)stages * kStdChunk;
+    L.off_bars = off; off += 256;
+    L.total = off;
+    return stages >= 3;
+}
+
+}  // namespace
+
+bool merge_staged_supported(const MergeParams& p, bool all_std_images) {
+    if (p.C != kC || p.bits != 256 || p.max_dn != 255.0 || !all_std_images) return false;
+    if ((int64_t)p.H * p.W < kTilePx) return false;
+    if (p.flat_bytes && !aligned(p.flat_std, 16)) return false;
+    StagedLayout L;
+    return make_layout(p, L);
+}
+
+// generic kernel on the ragged tail (hdr_merge.cu)
+int launch_merge_generic_range(const MergeParams& p, int64_t first_item, cudaStream_t stream);
+
+int launch_merge_staged(const MergeParams& p, cudaStream_t stream) {
+    StagedLayout L;
+    if (!make_layout(p, L)) return CL_ERR_UNSUPPORTED;
+    const int64_t n_px = (int64_t)p.H * p.W;
+    const int n_tiles = (int)(n_px / kTilePx);
+    int grid = sm_count();
+    if (grid > n_tiles) grid = n_tiles;
+    auto launch = [&](auto kernel) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)L.total);
+        if (e != cudaSuccess) return cuda_status(e);
+        kernel<<<grid, kThreads, L.total, stream>>>(p, L, n_tiles);
+        return launched();
+    };
+    int st;
+    if (p.n <= 8) st = launch(merge_staged_kernel<8>);
+    else if (p.n <= 16) st = launch(merge_staged_kernel<16>);
+    else st = launch(merge_staged_kernel<32>);
+    if (st != CL_OK) return st;
+    // pixels past the last full tile (< 512) go through the generic kernel; both kernels run
+    // identical arithmetic, so the seam is invisible
+    const int64_t tail_first_sample = (int64_t)n_tiles * kTilePx * kC;
+    if (tail_first_sample < n_px * kC) return launch_merge_generic_range(p, tail_first_sample / 4, stream);
+    return CL_OK;
+}
+
+}  // namespace cl

@@ -1,0 +1,356 @@
+"""``Measurand``: a value tensor and its uncertainty tensor with first-order error propagation.
+
+Mirror of the reference's operator API (``modules/measurand.py:26-761``; factory
+``modules/measurand_factory.py:10-14``) on ONE backend: torch tensors, CUDA for the hot path.
+``.val`` / ``.std`` are ``torch.Tensor`` (the reference's are NumPy/CuPy arrays); NumPy arrays and
+Python scalars are accepted at the constructor and moved to the default device.
+
+Hot-path methods call the sm_100a kernels through ``ops`` (C ABI), and raise when the tensors
+are not on a CUDA device -- there is no CPU implementation of them:
+    linearize, apply_gaussian_weight, filter_larger_than_by_map, normalize_by_map.
+The remaining operator surface (``+ - * / **``, logs, thresholds, statistics) are thin torch
+expressions following the reference formulae literally; they work on any device.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from typing import List, Optional, Union
+
+import numpy as np
+import torch
+
+from . import general_functions as gf
+from . import ops
+from .settings import GlobalSettings as gs
+
+ScalarType = (int, float)
+
+
+def _to_tensor(x, what: str):
+    if isinstance(x, torch.Tensor):
+        return x
+    if isinstance(x, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(x)).to(gs.device())
+    if isinstance(x, ScalarType) and not isinstance(x, bool):
+        return torch.tensor([x], dtype=torch.float64, device=gs.device())   # measurand.py:703-707
+    raise TypeError(what)
+
+
+def _flat_roi():
+    """ROI of measurand.py:569-576 with repair R7 (``int()`` the float bounds)."""
+    p = gs.FF_MID_PERCENTAGE
+    dx, dy = math.floor(gs.IM_SIZE_X * p), math.floor(gs.IM_SIZE_Y * p)
+    start = (math.floor(1 / p) - 1) / 2
+    return int(start * dx), int((start + 1) * dx), int(start * dy), int((start + 1) * dy)
+
+
+class Measurand:
+    """Value + uncertainty pair.  The last dimension holds independent channels."""
+
+    backend = "torch"
+    ArrayType = torch.Tensor
+    InputType = (torch.Tensor, np.ndarray, int, float)
+
+    def __init__(self, val=None, std=None, use_cupy=None):
+        # `use_cupy` is accepted for signature compatibility (measurand_factory.py:10) and ignored:
+        # the NumPy/CuPy dispatch is gone.
+        if val is not None and (isinstance(val, bool) or not isinstance(val, self.InputType)):
+            raise TypeError('Invalid value type.')
+        if std is not None and (isinstance(std, bool) or not isinstance(std, self.InputType)):
+            raise TypeError('Invalid std type')
+        if val is not None:
+            val = _to_tensor(val, 'Invalid value type.')
+        if std is not None:
+            std = _to_tensor(std, 'Invalid std type')
+        if val is not None and std is not None:
+            if std.device != val.device:
+                std = std.to(val.device)
+            if val.shape != std.shape:
+                raise ValueError('Value and std shapes must match.')
+        self._val = val
+        self._std = std
+        self._channels = None if val is None else torch.arange(0, val.ndim)
+
+    # ---- attributes (measurand.py:49-84) ----
+    @property
+    def val(self):
+        return self._val
+
+    @val.setter
+    def val(self, value):
+        if isinstance(value, np.ndarray):
+            value = _to_tensor(value, '')
+        if value is not None and not isinstance(value, torch.Tensor):
+            raise TypeError(f"val must be an array or None, got {type(value)} instead.")
+        self._val = value
+        self._channels = torch.arange(0, 0 if value is None else value.ndim)
+
+    @property
+    def std(self):
+        return self._std
+
+    @std.setter
+    def std(self, value):
+        if isinstance(value, np.ndarray):
+            value = _to_tensor(value, '')
+        if value is not None and not isinstance(value, torch.Tensor):
+            raise TypeError(f"std must be an array or None, got {type(value)} instead.")
+        self._std = value
+
+    @property
+    def channels(self):
+        return self._channels
+
+    @channels.setter
+    def channels(self, _):
+        raise AttributeError("Channels is a read-only attribute, based on the shape of val array.")
+
+    def __repr__(self):
+        vs = tuple(self.val.shape) if self.val is not None else 'None'
+        ss = tuple(self.std.shape) if self.std is not None else 'None'
+        return f'Measurand(value.shape= {vs}, std.shape= {ss}, values={self.val})'
+
+    def __copy__(self):
+        return self.__class__(self.val, self.std)
+
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            setattr(new, k, v.clone() if isinstance(v, torch.Tensor) else copy.deepcopy(v, memo))
+        return new
+
+    def numpy(self):
+        """Host copies ``(val, std)`` as NumPy arrays (std may be None)."""
+        v = None if self.val is None else self.val.detach().cpu().numpy()
+        s = None if self.std is None else self.std.detach().cpu().numpy()
+        return v, s
+
+    def to(self, device):
+        return self.__class__(None if self.val is None else self.val.to(device),
+                              None if self.std is None else self.std.to(device))
+
+    # ---- operand normalisation (measurand.py:281-302) ----
+    def _normalize_input(self, other):
+        if isinstance(other, Measurand):
+            normalized = other
+        elif isinstance(other, self.InputType) and not isinstance(other, bool):
+            normalized = self.__class__(other)
+            if normalized.val.device != self.val.device:
+                normalized = normalized.to(self.val.device)
+        else:
+            raise TypeError('Invalid other type.')
+        use_std = self.std is not None or normalized.std is not None
+        return normalized, use_std
+
+    def _binary_operands(self, other):
+        normalized, use_std = self._normalize_input(other)
+        x1, x2 = self.val, normalized.val
+        if not gf.is_broadcastable(x1.shape, x2.shape):
+            raise ValueError('Measurands are not broadcastable.')
+        s1 = s2 = None
+        if use_std:
+            s1 = self.std if self.std is not None else torch.zeros_like(x1)
+            s2 = normalized.std if normalized.std is not None else torch.zeros_like(x2)
+        return x1, x2, s1, s2, use_std
+
+    # ---- arithmetic with uncertainty propagation (measurand.py:106-241) ----
+    def __add__(self, other):
+        x1, x2, s1, s2, use_std = self._binary_operands(other)
+        return self.__class__(x1 + x2, torch.sqrt(s1 ** 2 + s2 ** 2) if use_std else None)
+
+    def __sub__(self, other):
+        x1, x2, s1, s2, use_std = self._binary_operands(other)
+        return self.__class__(x1 - x2, torch.sqrt(s1 ** 2 + s2 ** 2) if use_std else None)
+
+    def __neg__(self):
+        return self.__class__(torch.negative(self.val), None if self.std is None else self.std.clone())
+
+    def __truediv__(self, other):
+        x1, x2, s1, s2, use_std = self._binary_operands(other)
+        if not use_std:
+            return self.__class__(x1 / x2, None)
+        u1 = s1 / x2
+        u2 = (x1 * s2) / (x2 ** 2)
+        return self.__class__(x1 / x2, torch.sqrt(u1 ** 2 + u2 ** 2))
+
+    def __mul__(self, other):
+        x1, x2, s1, s2, use_std = self._binary_operands(other)
+        if not use_std:
+            return self.__class__(x1 * x2, None)
+        return self.__class__(x1 * x2, torch.sqrt((x1 * s2) ** 2 + (x2 * s1) ** 2))
+
+    def __rmul__(self, other):
+        return self * self.__class__(other)
+
+    def __pow__(self, other):
+        x1, x2, s1, s2, use_std = self._binary_operands(other)
+        if not use_std:
+            return self.__class__(x1 ** x2, None)
+        u1 = x2 * x1 ** (x2 - 1)
+        u2 = torch.log(x1) * x1 ** x2
+        return self.__class__(x1 ** x2, torch.sqrt((u1 * s1) ** 2 + (u2 * s2) ** 2))
+
+    def log_e(self):
+        # literal reference formula (measurand.py:258), questionable maths kept (D18)
+        res = torch.log(self.val)
+        return self.__class__(res, None if self.std is None else self.std / torch.log(self.val))
+
+    def log_10(self):
+        res = torch.log10(self.val)
+        if self.std is None:
+            return self.__class__(res, None)
+        return self.__class__(res, self.std / (self.val * (math.log(5) + math.log(2))))
+
+    def zeros_like_measurand(self):
+        return self.__class__(None if self.val is None else torch.zeros_like(self.val),
+                              None if self.std is None else torch.zeros_like(self.std))
+
+    # ---- statistics / selection (measurand.py:318-469); torch expressions, not hot path ----
+    def compute_dimension_statistics(self, axis=None):
+        values = self.val
+        dims = None if axis is None else (axis if isinstance(axis, (tuple, list)) else (axis,))
+
+        def nansum(t):
+            return torch.nansum(t) if dims is None else torch.nansum(t, dim=dims)
+
+        def nanmean(t):
+            return torch.nanmean(t) if dims is None else torch.nanmean(t, dim=dims)
+
+        std_mean = None
+        if self.std is None:
+            mean = nanmean(values)
+            centre = mean if dims is None else nanmean(values).reshape(
+                [1 if i in [d % values.ndim for d in dims] else s for i, s in enumerate(values.shape)])
+            spread = torch.sqrt(nanmean((values - centre) ** 2))
+        else:
+            weights = 1 / self.std
+            sum_w = nansum(weights)
+            mean = nansum(values * weights) / sum_w
+            centre = mean if dims is None else mean.reshape(
+                [1 if i in [d % values.ndim for d in dims] else s for i, s in enumerate(values.shape)])
+            spread = torch.sqrt(nansum(weights * (values - centre) ** 2) / sum_w)
+            std_mean = nanmean(self.std)
+        return {"mean": mean, "std": spread, "error": std_mean}
+
+    def extract(self, dims: Optional[Union[int, List[int]]] = None, axis: Optional[int] = None):
+        target = [dims] if type(dims) is int else dims
+        index = torch.as_tensor(target, dtype=torch.long, device=self.val.device)
+        if axis is None:
+            value = self.val.reshape(-1)[index]
+            std = None if self.std is None else self.std.reshape(-1)[index]
+        else:
+            value = torch.index_select(self.val, axis, index)
+            std = None if self.std is None else torch.index_select(self.std, axis, index)
+        return self.__class__(value, std)
+
+    def apply_thresholds(self, lower: Optional[List[Optional[float]]] = None,
+                         upper: Optional[List[Optional[float]]] = None):
+        """In place: values outside the per-channel [lower, upper] become NaN (measurand.py:375-428)."""
+        n = self.val.shape[-1]
+        lower = [None] * n if lower is None else lower
+        upper = [None] * n if upper is None else upper
+        if len(lower) != n or len(upper) != n:
+            raise ValueError("The length of 'lower' and 'upper' must match the size of the independent axis.")
+        value = self.val
+        lo = torch.tensor([-math.inf if l is None else l for l in lower], dtype=value.dtype, device=value.device)
+        hi = torch.tensor([math.inf if u is None else u for u in upper], dtype=value.dtype, device=value.device)
+        mask = (value < lo) | (value > hi)
+        value[mask] = math.nan
+        self.val = value
+        if self.std is not None:
+            self.std[mask] = math.nan
+
+    def compute_channel_histogram(self, bins: int, included_range=None, channels=None, use_std=False):
+        """measurand.py:430-469.  Small host-side reduction (NumPy) -- presentation path."""
+        if channels is None:
+            channels = list(range(gs.NUM_OF_CHS))
+        val, std = self.numpy()
+        out = {}
+        for c in channels:
+            v = val[..., c]
+            mask = np.isfinite(v)
+            weights = None
+            if use_std:
+                s = std[..., c]
+                mask = np.logical_and(mask, s != 0)
+                weights = 1 / s[mask]
+            out[c] = np.histogram(v[mask], bins=bins, range=included_range, weights=weights)
+        return out
+
+    # ---- hot path: sm_100a kernels through the C ABI ----
+    def linearize(self, ICRF, ICRF_diff=None):
+        """LUT linearisation (measurand.py:471-541, repair R1).  ICRF: (BITS, C) tensor/array, or
+        (BITS,) for single-channel data; ICRF_diff: its derivative for uncertainty propagation."""
+        dev = self.val.device
+        icrf = torch.as_tensor(ICRF, device=dev)
+        diff = None if ICRF_diff is None else torch.as_tensor(ICRF_diff, device=dev)
+        val = self.val
+        single = val.shape[-1] < 2                      # measurand.py:482-485
+        if single and icrf.ndim == 2:
+            if icrf.shape[1] != 1:
+                raise NotImplementedError("single-channel data with a multi-channel ICRF")
+            # NumPy's ICRF[idx] with a (BITS, 1) table appends a unit axis; reproduce the shape
+            out_v, out_s = ops.linearize(val, self.std, icrf[:, 0], None if diff is None else diff[:, 0], gs.MAX_DN)
+            return self.__class__(out_v.unsqueeze(-1), None if out_s is None else out_s.unsqueeze(-1))
+        if not single and icrf.ndim != 2:
+            raise IndexError("too many indices for array: a multi-channel image needs a (BITS, C) ICRF")
+        out_v, out_s = ops.linearize(val, self.std, icrf, diff, gs.MAX_DN)
+        return self.__class__(out_v, out_s)
+
+    def apply_gaussian_weight(self):
+        """``w = e^(-30 (v-0.5)^2)``, ``dw = -60 (v-0.5) w`` (measurand.py:606-618)."""
+        return ops.gaussian_weight(self.val)
+
+    def filter_larger_than_by_map(self, map: 'Measurand', threshold_value: float):
+        """Median replacement where ``map.val > threshold`` (measurand.py:543-557, repairs R5/R6)."""
+        v, s = ops.bad_pixel_filter(self.val, self.std, map.val, threshold_value, gs.MEDIAN_FILTER_KERNEL_SIZE)
+        return self.__class__(v, s)
+
+    def normalize_by_map(self, map: 'Measurand', roi=None):
+        """Flat-field correction with uncertainty (measurand.py:559-604, repair R7).  ``roi`` =
+        (row0, row1, col0, col1); default reproduces the reference's literal ROI formula."""
+        roi = _flat_roi() if roi is None else roi
+        means = ops.flat_roi_means(map.val, map.std, roi, gs.MAX_DN)
+        v, s = ops.flat_field_normalize(self.val, self.std, map.val, map.std, means)
+        return self.__class__(v, s)
+
+    # ---- statics (measurand.py:620-681) ----
+    @staticmethod
+    def compute_difference(x: 'Measurand', y: 'Measurand', multiplier: float):
+        cls = x.__class__
+        scale_term = multiplier * y.val
+        abs_diff = x.val - scale_term
+        rel_diff = abs_diff / scale_term
+        use_std = x.std is not None or y.std is not None
+        if not use_std:
+            return cls(abs_diff, None), cls(rel_diff, None)
+        x_std = x.std if x.std is not None else torch.zeros_like(x.val)
+        y_std = y.std if y.std is not None else torch.zeros_like(y.val)
+        abs_std = torch.sqrt(x_std ** 2 + (multiplier * y_std) ** 2)
+        rel_std = torch.sqrt((x_std / (multiplier * y.val)) ** 2
+                             + ((y_std * x.val) / (multiplier * y.val ** 2)) ** 2)
+        return cls(abs_diff, abs_std), cls(rel_diff, rel_std)
+
+    @staticmethod
+    def interpolate(x0: 'Measurand', x1: 'Measurand', y0: float, y1: float, y: float):
+        cls = x0.__class__
+        res = (x0.val * (y1 - y) + x1.val * (y - y0)) / (y1 - y0)
+        if x0.std is None and x1.std is None:
+            return cls(res, None)
+        s0 = x0.std if x0.std is not None else torch.zeros_like(res)
+        s1 = x1.std if x1.std is not None else torch.zeros_like(res)
+        # literal reference formula (measurand.py:679; the stds are not squared -- D18)
+        return cls(res, torch.sqrt(s0 * ((y1 - y) / (y1 - y0)) ** 2 + s1 * ((y - y0) / (y1 - y0)) ** 2))
+
+
+# names the reference exports
+AbstractMeasurand = Measurand
+NumpyMeasurand = Measurand
+
+
+def MeasurandFactory(val=None, std=None, use_cupy=True):
+    """``Measurand(val, std, use_cupy=...)`` factory of measurand_factory.py:10-14; the flag is
+    accepted and ignored (single backend)."""
+    return Measurand(val, std)

@@ -1,0 +1,479 @@
+"""Tensor-level operators: CUDA torch tensors in, CUDA torch tensors out.
+
+Each function checks its arguments, allocates outputs / scratch with torch (the C ABI never
+allocates), and enqueues the kernels of ``libcamlin_b200.so`` on torch's current CUDA stream.
+The main ones are also registered as PyTorch custom ops (``torch.ops.camera_linearity.*``) at
+the bottom of this file.  There is no CPU implementation: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import HdrMergeArgs, IcrfProblem, check
+
+Tensor = torch.Tensor
+
+
+# ------------------------------------------------------------------------------------- helpers
+def _require_cuda(*tensors: Optional[Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"expected a torch.Tensor, got {type(t)}")
+        if not t.is_cuda:
+            raise RuntimeError("camera_linearity_b200 operators run on CUDA tensors only "
+                               "(no CPU fallback); move the data to the GPU first")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("all tensors must live on the same CUDA device")
+    if dev is None:
+        raise RuntimeError("no CUDA tensor given")
+    return dev
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f64c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    return t.contiguous()
+
+
+def _dn_view(t: Tensor) -> Tuple[Tensor, int]:
+    """Integer image -> (contiguous tensor whose bytes are uint8/uint16 DNs, bytes per DN)."""
+    if t.dtype == torch.uint8:
+        return t.contiguous(), 1
+    if t.dtype in (torch.uint16, torch.int16):
+        return t.contiguous(), 2
+    raise TypeError(f"digital-number images must be uint8 or uint16, got {t.dtype}")
+
+
+def _lut_pair(icrf: Tensor, icrf_diff: Optional[Tensor], channels: int):
+    icrf = _f64c(icrf)
+    if icrf.ndim == 1:
+        icrf = icrf.reshape(-1, 1)
+    if icrf.ndim != 2 or icrf.shape[1] != channels:
+        raise ValueError(f"ICRF must have shape (BITS, {channels}); got {tuple(icrf.shape)}")
+    if icrf_diff is not None:
+        icrf_diff = _f64c(icrf_diff)
+        if icrf_diff.ndim == 1:
+            icrf_diff = icrf_diff.reshape(-1, 1)
+        if icrf_diff.shape != icrf.shape:
+            raise ValueError("ICRF_diff must have the same shape as ICRF")
+    return icrf, icrf_diff
+
+
+# ------------------------------------------------------------------------------------- K1
+def linearize(val: Tensor, std: Optional[Tensor], icrf: Tensor, icrf_diff: Optional[Tensor] = None,
+              max_dn: float = 255.0, return_bins: bool = False):
+    """``out[..., c] = ICRF[bin(val[..., c]), c]`` (+ ``ICRF_diff[bin] * std``); K1 of DESIGN.md.
+
+    val: integer DN image (uint8 / uint16) or floating image in [0, 1]; the last dimension is the
+    channel axis and must match the ICRF's second dimension (a 1-D ICRF = one channel).
+    """
+    _require_cuda(val, std, icrf, icrf_diff)
+    lib = _lib.load()
+    channels = 1 if icrf.ndim == 1 else int(icrf.shape[1])
+    if val.ndim == 0 or (channels > 1 and val.shape[-1] != channels):
+        raise ValueError(f"last dimension of val {tuple(val.shape)} must equal the ICRF channel count {channels}")
+    lut, dlut = _lut_pair(icrf, icrf_diff, channels)
+    bits = int(lut.shape[0])
+    use_std = std is not None and dlut is not None
+    std_c = _f64c(std) if use_std else None
+    if use_std and std_c.shape != val.shape:
+        raise ValueError("Value and std shapes must match.")
+    n = val.numel()
+    out_val = torch.empty(val.shape, dtype=torch.float64, device=val.device)
+    out_std = torch.empty_like(out_val) if use_std else None
+    bins = None
+    if val.dtype.is_floating_point:
+        v = _f64c(val)
+        if return_bins:
+            bins = torch.empty(val.shape, dtype=torch.int16, device=val.device)
+        check(lib.cl_linearize_f64(_ptr(v), float(max_dn), _ptr(std_c), _ptr(lut),
+                                   _ptr(dlut) if use_std else None, _ptr(out_val), _ptr(out_std),
+                                   _ptr(bins), n, channels, bits, _stream()), "cl_linearize_f64")
+    else:
+        v, dn_bytes = _dn_view(val)
+        check(lib.cl_linearize_dn(_ptr(v), dn_bytes, _ptr(std_c), _ptr(lut),
+                                  _ptr(dlut) if use_std else None, _ptr(out_val), _ptr(out_std), n,
+                                  channels, bits, _stream()), "cl_linearize_dn")
+        if return_bins:
+            bins = v
+    if return_bins:
+        return out_val, out_std, bins
+    return out_val, out_std
+
+
+# ------------------------------------------------------------------------------------- K2
+def flat_roi_means(flat: Tensor, flat_std: Tensor, roi: Tuple[int, int, int, int],
+                   max_dn: float = 255.0) -> Tensor:
+    """ROI means ``[m_0..m_{C-1}, ms_0..ms_{C-1}]`` of a flat field (measurand.py:561-583)."""
+    _require_cuda(flat, flat_std)
+    lib = _lib.load()
+    if flat.ndim != 3:
+        raise ValueError("flat field must be (H, W, C)")
+    h, w, c = (int(s) for s in flat.shape)
+    if flat.dtype.is_floating_point:
+        f, fbytes = _f64c(flat), 8
+    else:
+        f, fbytes = _dn_view(flat)
+    fs = _f64c(flat_std)
+    out = torch.empty(2 * c, dtype=torch.float64, device=flat.device)
+    ws_bytes = lib.cl_flat_roi_means_workspace_bytes(h, w, c)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=flat.device)
+    r0, r1, c0, c1 = (int(x) for x in roi)
+    check(lib.cl_flat_roi_means(_ptr(f), fbytes, float(max_dn), _ptr(fs), h, w, c, r0, r1, c0, c1,
+                                _ptr(out), _ptr(ws), ws_bytes, _stream()), "cl_flat_roi_means")
+    return out
+
+
+def hdr_merge(dn: Sequence[Tensor], std: Optional[Sequence[Optional[Tensor]]],
+              exposures: Sequence[float], icrf: Tensor, icrf_diff: Tensor, *,
+              std_lut: Optional[Tensor] = None,
+              darks: Optional[Sequence[Optional[Tensor]]] = None,
+              dark_scales: Optional[Sequence[float]] = None, dark_threshold: float = 0.0,
+              median_kernel: int = 3, flat: Optional[Tensor] = None,
+              flat_std: Optional[Tensor] = None, flat_means: Optional[Tensor] = None,
+              algo: int = 0, out: Optional[Tuple[Tensor, Tensor]] = None,
+              workspace: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """Fused weighted HDR merge of N exposures (K2 of DESIGN.md); returns (radiance, std).
+
+    dn[k]: (H, W, C) uint8/uint16 exposures in ascending exposure order; std[k]: float64
+    uncertainty images (an entry may be None when ``std_lut`` is given); darks[k]: the dark frame
+    selected for exposure k or None; flat / flat_std / flat_means: optional flat-field epilogue.
+    """
+    n = len(dn)
+    if n < 1 or n > _lib.CL_MAX_EXPOSURES:
+        raise ValueError(f"hdr_merge supports 1..{_lib.CL_MAX_EXPOSURES} exposures, got {n}")
+    if len(exposures) != n:
+        raise ValueError("one exposure time per image is required")
+    _require_cuda(*dn, icrf, icrf_diff, std_lut, flat, flat_std, flat_means)
+    lib = _lib.load()
+    first, dn_bytes = _dn_view(dn[0])
+    if first.ndim != 3:
+        raise ValueError("exposures must be (H, W, C) images")
+    h, w, c = (int(s) for s in first.shape)
+    keep: List[Tensor] = []            # keeps converted tensors alive until the launch is enqueued
+
+    def _img(t: Tensor) -> Tensor:
+        v, b = _dn_view(t)
+        if b != dn_bytes or tuple(v.shape) != (h, w, c):
+            raise ValueError("all exposures / dark frames must share dtype and shape")
+        keep.append(v)
+        return v
+
+    dn_c = [_img(t) for t in dn]
+    lut, dlut = _lut_pair(icrf, icrf_diff, c)
+    if dlut is None:
+        raise ValueError("ICRF_diff is required for the merge")
+    bits = int(lut.shape[0])
+    std_c: List[Optional[Tensor]] = []
+    for k in range(n):
+        s = None if std is None else std[k]
+        if s is None:
+            if std_lut is None:
+                raise ValueError(f"exposure {k} has no uncertainty image and no std_lut was given")
+            std_c.append(None)
+        else:
+            _require_cuda(s)
+            s = _f64c(s)
+            if tuple(s.shape) != (h, w, c):
+                raise ValueError("Value and std shapes must match.")
+            keep.append(s)
+            std_c.append(s)
+    sl = None
+    if std_lut is not None:
+        sl, _ = _lut_pair(std_lut, None, c)
+        if sl.shape[0] != bits:
+            raise ValueError("std_lut must have as many rows as the ICRF")
+    dark_c: List[Optional[Tensor]] = [None] * n
+    if darks is not None:
+        if len(darks) != n:
+            raise ValueError("darks must have one entry (or None) per exposure")
+        for k, d in enumerate(darks):
+            if d is not None:
+                _require_cuda(d)
+                dark_c[k] = _img(d)
+    scales = [1.0] * n if dark_scales is None else [float(x) for x in dark_scales]
+
+    args = HdrMergeArgs()
+    args.n_exposures, args.height, args.width, args.channels = n, h, w, c
+    args.dn_bytes, args.bits = dn_bytes, bits
+    dn_arr = (C.c_void_p * n)(*[t.data_ptr() for t in dn_c])
+    std_arr = (C.c_void_p * n)(*[_ptr(t) for t in std_c])
+    dark_arr = (C.c_void_p * n)(*[_ptr(t) for t in dark_c])
+    t_arr = (C.c_double * n)(*[float(x) for x in exposures])
+    sc_arr = (C.c_double * n)(*scales)
+    args.dn = C.cast(dn_arr, C.POINTER(C.c_void_p))
+    args.std = C.cast(std_arr, C.POINTER(C.c_void_p))
+    args.dark = C.cast(dark_arr, C.POINTER(C.c_void_p))
+    args.exposure_s = C.cast(t_arr, C.POINTER(C.c_double))
+    args.dark_scale = C.cast(sc_arr, C.POINTER(C.c_double))
+    args.lut, args.dlut, args.std_lut = _ptr(lut), _ptr(dlut), _ptr(sl)
+    args.dark_threshold = float(dark_threshold)
+    args.median_kernel = int(median_kernel)
+    fv = fs = fm = None
+    if flat is not None:
+        if flat_std is None or flat_means is None:
+            raise ValueError("flat-field correction needs flat, flat_std and flat_means")
+        if flat.dtype.is_floating_point:
+            fv, fbytes = _f64c(flat), 8
+        else:
+            fv, fbytes = _dn_view(flat)
+        fs, fm = _f64c(flat_std), _f64c(flat_means)
+        if tuple(fv.shape) != (h, w, c) or tuple(fs.shape) != (h, w, c) or fm.numel() != 2 * c:
+            raise ValueError("flat field shapes must match the exposures; flat_means must be (2C,)")
+        args.flat_bytes = fbytes
+        args.flat, args.flat_std, args.flat_means = _ptr(fv), _ptr(fs), _ptr(fm)
+    else:
+        args.flat_bytes = 0
+    if out is None:
+        out_val = torch.empty((h, w, c), dtype=torch.float64, device=first.device)
+        out_std = torch.empty_like(out_val)
+    else:
+        out_val, out_std = out
+        _require_cuda(out_val, out_std)
+        for o in (out_val, out_std):
+            if o.dtype != torch.float64 or tuple(o.shape) != (h, w, c) or not o.is_contiguous():
+                raise ValueError("out tensors must be contiguous float64 (H, W, C)")
+    args.out_val, args.out_std = _ptr(out_val), _ptr(out_std)
+    args.algo = int(algo)
+    ws_bytes = lib.cl_hdr_merge_workspace_bytes(C.byref(args))
+    ws = workspace
+    if ws_bytes and (ws is None or ws.numel() * ws.element_size() < ws_bytes):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=first.device)
+    check(lib.cl_hdr_merge(C.byref(args), _ptr(ws) if ws_bytes else None, ws_bytes, _stream()),
+          "cl_hdr_merge")
+    return out_val, out_std
+
+
+def gaussian_weight(val: Tensor) -> Tuple[Tensor, Tensor]:
+    """``apply_gaussian_weight`` (measurand.py:606-618): returns (w, dw)."""
+    _require_cuda(val)
+    lib = _lib.load()
+    v = _f64c(val)
+    w = torch.empty_like(v)
+    dw = torch.empty_like(v)
+    check(lib.cl_gaussian_weight(_ptr(v), _ptr(w), _ptr(dw), v.numel(), _stream()), "cl_gaussian_weight")
+    return w, dw
+
+
+def bad_pixel_filter(val: Tensor, std: Optional[Tensor], dark_val: Tensor, threshold: float,
+                     kernel: int) -> Tuple[Tensor, Optional[Tensor]]:
+    """``filter_larger_than_by_map`` (measurand.py:543-557) on float64 (H, W, C) images."""
+    _require_cuda(val, std, dark_val)
+    lib = _lib.load()
+    if val.ndim != 3:
+        raise ValueError("bad_pixel_filter expects (H, W, C) images")
+    v, s, d = _f64c(val), _f64c(std), _f64c(dark_val)
+    if d.shape != v.shape:
+        d = d.expand_as(v).contiguous()
+    h, w, c = (int(x) for x in v.shape)
+    out_v = torch.empty_like(v)
+    out_s = torch.empty_like(v) if s is not None else None
+    check(lib.cl_bad_pixel_filter(_ptr(v), _ptr(s), _ptr(d), float(threshold), int(kernel), h, w, c,
+                                  _ptr(out_v), _ptr(out_s), _stream()), "cl_bad_pixel_filter")
+    return out_v, out_s
+
+
+def flat_field_normalize(val: Tensor, std: Tensor, flat_val: Tensor, flat_std: Tensor,
+                         flat_means: Tensor) -> Tuple[Tensor, Tensor]:
+    """``normalize_by_map`` (measurand.py:559-604) given the ROI means."""
+    _require_cuda(val, std, flat_val, flat_std, flat_means)
+    lib = _lib.load()
+    v, s, fv, fs, fm = (_f64c(t) for t in (val, std, flat_val, flat_std, flat_means))
+    c = int(v.shape[-1])
+    out_v, out_s = torch.empty_like(v), torch.empty_like(v)
+    check(lib.cl_flat_field_normalize(_ptr(v), _ptr(s), _ptr(fv), _ptr(fs), _ptr(fm), v.numel(), c,
+                                      _ptr(out_v), _ptr(out_s), _stream()), "cl_flat_field_normalize")
+    return out_v, out_s
+
+
+# ------------------------------------------------------------------------------------- K3
+def welford_update(frames: Tensor, mean: Tensor, m2: Tensor, count0: int,
+                   icrf: Optional[Tensor] = None, max_dn: float = 255.0) -> int:
+    """Fold ``frames`` (F, H, W, C) uint8 into the running (mean, m2) state in place -- the
+    reference's sequential recurrence (video_processing.py:205-208), bit-identical float64."""
+    _require_cuda(frames, mean, m2, icrf)
+    lib = _lib.load()
+    if frames.dtype != torch.uint8 or frames.ndim < 2:
+        raise TypeError("frames must be a uint8 tensor (F, ...)")
+    fr = frames.contiguous()
+    f = int(fr.shape[0])
+    n = fr[0].numel() if f else mean.numel()
+    c = int(fr.shape[-1])
+    for s in (mean, m2):
+        if s.dtype != torch.float64 or not s.is_contiguous() or s.numel() != n:
+            raise ValueError("mean / m2 must be contiguous float64 with one element per sample")
+    lut = None
+    if icrf is not None:
+        lut, _ = _lut_pair(icrf, None, c)
+    check(lib.cl_welford_update(_ptr(fr), f, n, c, _ptr(lut), float(max_dn), _ptr(mean), _ptr(m2),
+                                int(count0), _stream()), "cl_welford_update")
+    return count0 + f
+
+
+def welford_finalize(mean: Tensor, m2: Optional[Tensor], count: int, max_dn: float = 255.0):
+    """Returns (sem float64 or None, mean_u8) -- video_processing.py:210-215 with repair R9."""
+    _require_cuda(mean, m2)
+    lib = _lib.load()
+    n = mean.numel()
+    sem = torch.empty_like(mean) if m2 is not None else None
+    mean_u8 = torch.empty(mean.shape, dtype=torch.uint8, device=mean.device)
+    check(lib.cl_welford_finalize(_ptr(mean), _ptr(m2), int(count), n, float(max_dn), _ptr(sem),
+                                  _ptr(mean_u8), _stream()), "cl_welford_finalize")
+    return sem, mean_u8
+
+
+def welford_stack(frames: Tensor, icrf: Optional[Tensor] = None, max_dn: float = 255.0,
+                  workspace: Optional[Tensor] = None):
+    """Mean / SEM / uint8 mean of a resident frame stack (F, H, W, C) uint8 (K3 of DESIGN.md)."""
+    _require_cuda(frames, icrf)
+    lib = _lib.load()
+    if frames.dtype != torch.uint8 or frames.ndim < 2:
+        raise TypeError("frames must be a uint8 tensor (F, ...)")
+    fr = frames.contiguous()
+    f = int(fr.shape[0])
+    if f < 1:
+        raise ValueError("at least one frame is required")
+    shape = tuple(fr.shape[1:])
+    n = fr[0].numel()
+    c = int(fr.shape[-1])
+    lut = None
+    if icrf is not None:
+        lut, _ = _lut_pair(icrf, None, c)
+    mean = torch.empty(shape, dtype=torch.float64, device=fr.device)
+    sem = torch.empty_like(mean)
+    mean_u8 = torch.empty(shape, dtype=torch.uint8, device=fr.device)
+    ws_bytes = lib.cl_welford_stack_workspace_bytes(f, n)
+    ws = workspace
+    if ws is None or ws.numel() * ws.element_size() < ws_bytes:
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=fr.device)
+    check(lib.cl_welford_stack(_ptr(fr), f, n, c, _ptr(lut), float(max_dn), _ptr(mean), _ptr(sem),
+                               _ptr(mean_u8), _ptr(ws), ws_bytes, _stream()), "cl_welford_stack")
+    return mean, sem, mean_u8
+
+
+# ------------------------------------------------------------------------------------- K4
+class IcrfEnergyPlan:
+    """Device-resident state of one calibration problem (one colour channel): pixel samples,
+    PCA basis, scratch.  ``partial()`` and ``finalize()`` map onto the C ABI calls so that a
+    multi-GPU driver can all-reduce the pair sums in between (parallel.py)."""
+
+    def __init__(self, dn_stack: Tensor, std_stack: Optional[Tensor], exposures, mean_icrf,
+                 pca_basis: Tensor, lower: int, upper: int, use_mean_icrf: bool, n_candidates: int):
+        dev = _require_cuda(dn_stack, std_stack, pca_basis)
+        self.lib = _lib.load()
+        if dn_stack.dtype != torch.uint8:
+            raise TypeError("the calibration value stack must be uint8 "
+                            "(ICRF_calibration_exposure.py:191 indexes the curve with it)")
+        if dn_stack.ndim != 3:
+            raise ValueError("image_stack must be a 3D CuPy array with shape (X, Y, N).")
+        n_exp = int(dn_stack.shape[2])
+        exposures = np.asarray(exposures, dtype=np.float64)
+        if exposures.ndim != 1 or exposures.size != n_exp:
+            raise ValueError("exposure_values must be a 1D CuPy array matching the third dimension of image_stack.")
+        if not 2 <= n_exp <= _lib.CL_MAX_PAIR_EXPOSURES:
+            raise ValueError(f"2..{_lib.CL_MAX_PAIR_EXPOSURES} exposures are supported, got {n_exp}")
+        self.dn = dn_stack.contiguous().reshape(-1, n_exp)
+        self.n_pixels = int(self.dn.shape[0])
+        self.std = None
+        if std_stack is not None:
+            if std_stack.shape != dn_stack.shape:
+                raise ValueError("Value and std shapes must match.")
+            self.std = _f64c(std_stack).reshape(-1, n_exp)
+        self.pca = _f64c(pca_basis)
+        self.datapoints = int(self.pca.shape[0])
+        self.n_pc = int(self.pca.shape[1])
+        self.mean = None if mean_icrf is None else _f64c(torch.as_tensor(mean_icrf, device=dev))
+        if self.n_pixels and int(self.dn.max()) >= self.datapoints:
+            raise IndexError("digital numbers exceed the curve length")
+        self.exposures = (C.c_double * n_exp)(*exposures.tolist())
+        self.n_real = int(n_candidates)
+        s_pad = max(32, (self.n_real + 31) // 32 * 32)
+        self.prob = IcrfProblem(s_pad, self.n_pc + (0 if use_mean_icrf else 1), self.datapoints,
+                                1 if use_mean_icrf else 0, int(lower), int(upper), n_exp,
+                                1 if self.std is not None else 0)
+        self.n_pairs = n_exp * (n_exp - 1) // 2
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.params = torch.zeros((s_pad, self.prob.n_params), **f64)
+        self.curves = torch.empty((s_pad, self.datapoints), **f64)
+        self.valid = torch.empty(s_pad, dtype=torch.int32, device=dev)
+        self.tables = torch.empty(self.lib.cl_icrf_tables_bytes(C.byref(self.prob)), dtype=torch.uint8, device=dev)
+        self.pair_acc = torch.empty((s_pad, self.n_pairs, 2), **f64)
+        self.energy = torch.empty(s_pad, **f64)
+        self.ws_bytes = self.lib.cl_icrf_energy_workspace_bytes(C.byref(self.prob), self.n_pixels)
+        self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev)
+
+    def set_params(self, params: Tensor) -> None:
+        """params: (S, n_params) -- one row per candidate (device or host)."""
+        p = torch.as_tensor(params, dtype=torch.float64)
+        if p.shape != (self.n_real, self.prob.n_params):
+            raise ValueError(f"params must be ({self.n_real}, {self.prob.n_params})")
+        self.params[: self.n_real].copy_(p, non_blocking=True)
+
+    def curves_and_tables(self) -> None:
+        check(self.lib.cl_icrf_curves(C.byref(self.prob), _ptr(self.mean), _ptr(self.pca), _ptr(self.params),
+                                      _ptr(self.curves), _ptr(self.valid), _ptr(self.tables), _stream()),
+              "cl_icrf_curves")
+
+    def partial(self) -> Tensor:
+        check(self.lib.cl_icrf_energy_partial(C.byref(self.prob), _ptr(self.tables), _ptr(self.dn), _ptr(self.std),
+                                              self.exposures, self.n_pixels, _ptr(self.pair_acc), _ptr(self.ws),
+                                              self.ws_bytes, _stream()), "cl_icrf_energy_partial")
+        return self.pair_acc
+
+    def finalize(self) -> Tensor:
+        check(self.lib.cl_icrf_energy_finalize(C.byref(self.prob), _ptr(self.pair_acc), _ptr(self.valid),
+                                               _ptr(self.energy), _stream()), "cl_icrf_energy_finalize")
+        return self.energy[: self.n_real]
+
+    def evaluate(self, params) -> Tensor:
+        """Energies (S,) of a population on this GPU's pixels (single-GPU path)."""
+        self.set_params(params)
+        self.curves_and_tables()
+        self.partial()
+        return self.finalize()
+
+
+# ------------------------------------------------------------------------------------- custom ops
+# Registered for discoverability / composability with torch.library; they call the functions above.
+@torch.library.custom_op("camera_linearity::linearize", mutates_args=(), device_types="cuda")
+def _op_linearize(val: Tensor, std: Optional[Tensor], icrf: Tensor, icrf_diff: Optional[Tensor],
+                  max_dn: float) -> List[Tensor]:
+    v, s = linearize(val, std, icrf, icrf_diff, max_dn)
+    return [v] if s is None else [v, s]
+
+
+@torch.library.custom_op("camera_linearity::hdr_merge", mutates_args=(), device_types="cuda")
+def _op_hdr_merge(dn: List[Tensor], std: List[Tensor], exposures: List[float], icrf: Tensor,
+                  icrf_diff: Tensor, algo: int) -> List[Tensor]:
+    v, s = hdr_merge(dn, std, exposures, icrf, icrf_diff, algo=algo)
+    return [v, s]
+
+
+@torch.library.custom_op("camera_linearity::welford_stack", mutates_args=(), device_types="cuda")
+def _op_welford_stack(frames: Tensor, icrf: Optional[Tensor], max_dn: float) -> List[Tensor]:
+    return list(welford_stack(frames, icrf, max_dn))
+
+
+@torch.library.custom_op("camera_linearity::gaussian_weight", mutates_args=(), device_types="cuda")
+def _op_gaussian_weight(val: Tensor) -> List[Tensor]:
+    return list(gaussian_weight(val))

@@ -1,0 +1,67 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink on the box,
+gloo in the CPU tests).
+
+K1-K3 shard by independent units (whole stacks, or row blocks of one stack) with no data-path
+collective.  K4 (calibration loss) has one real exchange: the per-(candidate, exposure-pair)
+numerator/denominator sums are all-reduced (SUM, float64, S x pairs x 2 values ~ 10 KB) once per
+DE generation; the gates and the nanmean are applied after the reduction, identically on every
+rank.  The energy itself is a mean of ratios and is NOT linear -- never all-reduce it.
+"""
+from __future__ import annotations
+
+import os
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def is_distributed() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def world_size() -> int:
+    return dist.get_world_size() if is_distributed() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if is_distributed() else 0
+
+
+def init_from_env(backend: str | None = None) -> Tuple[int, int, int]:
+    """Initialise the default process group from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*.
+    Returns (rank, world_size, local_rank).  A single process needs no group."""
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rk = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if ws > 1 and not is_distributed():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend=backend, rank=rk, world_size=ws)
+    return rk, ws, local
+
+
+def shard_range(n_units: int, rank_: int | None = None, world: int | None = None) -> Tuple[int, int]:
+    """Contiguous, balanced [lo, hi) slice of ``n_units`` independent units for this rank."""
+    r = rank() if rank_ is None else rank_
+    w = world_size() if world is None else world
+    base, extra = divmod(n_units, w)
+    lo = r * base + min(r, extra)
+    return lo, lo + base + (1 if r < extra else 0)
+
+
+def shard_rows(height: int, halo: int = 0, rank_: int | None = None, world: int | None = None):
+    """Row block [lo, hi) of an image for this rank plus the input rows [src_lo, src_hi) it must
+    read: a ``halo``-row apron (K // 2 for the K x K bad-pixel median) clipped at the borders."""
+    lo, hi = shard_range(height, rank_, world)
+    return lo, hi, max(0, lo - halo), min(height, hi + halo)
+
+
+def allreduce_pair_sums(pair_acc: torch.Tensor) -> torch.Tensor:
+    """In-place SUM all-reduce of the K4 pair sums (float64; counts are exact below 2^53)."""
+    if world_size() > 1:
+        dist.all_reduce(pair_acc, op=dist.ReduceOp.SUM)
+    return pair_acc

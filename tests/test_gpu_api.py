@@ -1,0 +1,105 @@
+"""The reference-facing Python API on the GPU: Measurand / ImageSet / ExposureSeries."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hdr_merge as om
+from oracle import linearize as ol
+from gpu_util import assert_rel, host, icrf_tables, synth_stack
+
+pytestmark = pytest.mark.gpu
+pytest.importorskip("camera_linearity_b200.ops")
+import camera_linearity_b200 as cl  # noqa: E402
+from camera_linearity_b200 import GlobalSettings as gs  # noqa: E402
+
+
+def _features(exposure, subject="s"):
+    return {"illumination": "bf", "magnification": "10x", "exposure": exposure, "subject": subject}
+
+
+def test_measurand_linearize_reference_property():
+    # tests/unit/test_measurand.py:447-467: each output channel only holds values of its LUT column
+    rng = np.random.default_rng(0)
+    for shape in [(6, 5, 3), (2, 3, 4, 2), (7, 1)]:
+        c = shape[-1]
+        icrf = np.stack([np.linspace(0, 1, 256) ** (i + 1) for i in range(c)], axis=1)
+        diff = ol.default_icrf_diff(icrf)
+        val = rng.random(shape)
+        m = cl.Measurand(val, val * 0.1)
+        out = m.linearize(icrf[:, 0], diff[:, 0]) if c == 1 else m.linearize(icrf, diff)
+        assert isinstance(out.val, torch.Tensor) and out.val.is_cuda
+        ev, es = ol.linearize(val, val * 0.1, icrf[:, 0] if c == 1 else icrf, diff[:, 0] if c == 1 else diff)
+        assert np.array_equal(host(out.val), ev) and np.array_equal(host(out.std), es)
+        for i in range(c):
+            assert np.isin(host(out.val)[..., i], icrf[:, i]).all()
+
+
+def test_measurand_hot_methods():
+    rng = np.random.default_rng(1)
+    val, std = rng.random((20, 24, 3)), rng.uniform(0.001, 0.02, (20, 24, 3))
+    m = cl.Measurand(val, std)
+    w, dw = m.apply_gaussian_weight()
+    ew, edw = om.gaussian_weight(val)
+    assert_rel(host(w), ew, 1e-14)
+    dark = cl.Measurand(rng.random(val.shape) * 0.1)
+    gs.configure(MEDIAN_FILTER_KERNEL_SIZE=3)
+    f = m.filter_larger_than_by_map(dark, 0.06)
+    ev, es = om.bad_pixel_filter(val, std, host(dark.val), 0.06, 3)
+    assert np.array_equal(host(f.val), ev) and np.array_equal(host(f.std), es)
+    gs.configure(IM_SIZE_X=20, IM_SIZE_Y=24, FF_MID_PERCENTAGE=0.2)
+    flat = cl.Measurand(rng.uniform(0.5, 1, val.shape), rng.uniform(0.001, 0.01, val.shape))
+    n = m.normalize_by_map(flat)
+    ev, es = om.normalize_by_map(val, std, host(flat.val), host(flat.std), om.flat_roi_bounds(20, 24, 0.2))
+    assert_rel(host(n.val), ev, 1e-13)
+    assert_rel(host(n.std), es, 1e-13)
+
+
+def test_exposure_series_process_hdr_image_in_memory():
+    rng = np.random.default_rng(2)
+    h, w = 48, 64
+    gs.configure(IM_SIZE_X=h, IM_SIZE_Y=w, DARK_THRESHOLD=0.05, MEDIAN_FILTER_KERNEL_SIZE=3, FF_MID_PERCENTAGE=0.2)
+    t = 0.005 * 2.0 ** np.arange(6)
+    dn, std = synth_stack(rng, h, w, 3, t)
+    icrf, diff = icrf_tables(3)
+    dark_t = [0.02, 0.08, 0.32]
+    dark_dn = []
+    for _ in dark_t:
+        d = rng.poisson(2.0, (h, w, 3)).astype(np.uint8)
+        hot = rng.uniform(size=d.shape) < 0.02
+        d[hot] = rng.integers(40, 200, int(hot.sum()))
+        dark_dn.append(d)
+    flat = np.clip(np.rint(rng.normal(180, 6, (h, w, 3))), 1, 255).astype(np.uint8)
+    fstd = rng.uniform(0.001, 0.01, (h, w, 3))
+
+    sets = [cl.ImageSet(value=dn[k], std=std[k], features=_features(float(t[k]))) for k in range(6)]
+    rng.shuffle(sets)
+    series = cl.ExposureSeries.from_multiple_image_sets(sets)[0]          # sorts by exposure
+    darks = [cl.ImageSet(value=d, features=_features(e, "dark")) for d, e in zip(dark_dn, dark_t)]
+    flats = [cl.ImageSet(value=flat, std=fstd, features=_features(0.0, "flat"))]
+    series.process_HDR_image(icrf, diff, dark_list=darks, flat_list=flats)
+    merged = series.merged_image_set
+    assert merged.is_HDR and merged.measurand.val.is_cuda
+
+    sel = [om.select_dark_field(float(tk), dark_t, 0.05) for tk in t]
+    hd = [None if s is None else om.dark_value_image(dark_dn[s[0]], s[1]) for s in sel]
+    ev, es = om.hdr_merge(dn, std, t, icrf, diff, darks=hd, dark_threshold=0.05, kernel=3, flat_val=flat / 255.0,
+                          flat_std=fstd, roi=om.flat_roi_bounds(h, w, 0.2))
+    assert_rel(host(merged.measurand.val), ev, 1e-11)
+    assert_rel(host(merged.measurand.std), es, 1e-11)
+
+    lin = series.linearize(icrf, diff)
+    ev1, es1 = ol.linearize(dn[0], std[0], icrf, diff)
+    assert np.array_equal(host(lin.input_image_sets[0].measurand.val), ev1)
+    assert np.array_equal(host(lin.input_image_sets[0].measurand.std), es1)
+
+
+def test_float_images_without_dn_are_requantised():
+    rng = np.random.default_rng(3)
+    t = [0.01, 0.02, 0.04]
+    dn, std = synth_stack(rng, 32, 32, 3, np.array(t))
+    icrf, diff = icrf_tables(3)
+    sets = [cl.ImageSet(value=dn[k] / 255.0, std=std[k], features=_features(t[k])) for k in range(3)]
+    series = cl.ExposureSeries(input_image_sets=sets)
+    series.process_HDR_image(icrf, diff, dark_list=[], flat_list=[])
+    ev, es = om.hdr_merge(dn, std, np.array(t), icrf, diff)
+    assert_rel(host(series.merged_image_set.measurand.val), ev, 1e-11)
