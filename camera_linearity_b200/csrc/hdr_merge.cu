@@ -222,6 +222,109 @@ int launch_generic(const MergeParams& p, bool tab_smem, int64_t first_item, cuda
     return launched();
 }
 
+// ---- bad-pixel work list (staged path) ------------------------------------------------------------
+// Streams the dark frames once (16 bytes per thread per load, SIMD byte compare) and appends the
+// index of every sample whose dark DN reaches the exposure's integer threshold.
+__device__ __forceinline__ void hot_append(const MergeParams& p, uint32_t sample) {
+    const uint32_t slot = atomicAdd(&p.hot_list[0], 1u);
+    if (slot < p.hot_cap) p.hot_list[kHotListHeader + slot] = sample;
+}
+
+__global__ void __launch_bounds__(256)
+dark_scan_kernel(const __grid_constant__ MergeParams p) {
+    const int64_t n = (int64_t)p.H * p.W * p.C;
+    const int64_t n_vec = n / 16;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int k = 0; k < p.n; ++k) {
+        if (!p.dark[k] || p.hot_dn[k] > 255u) continue;
+        const uint32_t thr = p.hot_dn[k] * 0x01010101u;
+        const uint4* src = reinterpret_cast<const uint4*>(p.dark[k]);
+        for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += stride) {
+            const uint4 q = __ldg(src + v);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t m = __vcmpgeu4(w[j], thr);
+                while (m) {
+                    const int b = (__ffs(m) - 1) >> 3;
+                    hot_append(p, (uint32_t)(v * 16 + j * 4 + b));
+                    m &= ~(0xFFu << (8 * b));
+                }
+            }
+        }
+        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(p.dark[k]);
+        for (int64_t i = n_vec * 16 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            if (bytes[i] >= p.hot_dn[k]) hot_append(p, (uint32_t)i);
+    }
+}
+
+// Full recomputation of one sample with the bad-pixel repair, same arithmetic (and the same
+// table values, recomputed on the fly) as the streaming kernels -> bit-identical to inline repair.
+template <typename DN>
+__device__ __noinline__ void recompute_sample(const MergeParams& p, int64_t i) {
+    const int C = p.C;
+    const int c = (int)(i % C);
+    const int64_t px = i / C;
+    const int y = (int)(px / p.W), x = (int)(px - (int64_t)y * p.W);
+    double S = 0.0;
+    uint32_t hot = 0;
+    for (int k = 0; k < p.n; ++k) {
+        const DN* img = reinterpret_cast<const DN*>(p.dn[k]);
+        uint32_t d = img[i];
+        if (p.dark[k] && (uint32_t) reinterpret_cast<const DN*>(p.dark[k])[i] >= p.hot_dn[k]) {
+            d = median_dn(img, y, x, c, p.H, p.W, C, p.K);
+            hot |= 1u << k;
+        }
+        double w, dw;
+        gaussian_weight(__ddiv_rn((double)d, p.max_dn), w, dw);
+        S += w;
+    }
+    const double rS = 1.0 / S;
+    double av = 0.0, as = 0.0;
+    for (int k = 0; k < p.n; ++k) {
+        const DN* img = reinterpret_cast<const DN*>(p.dn[k]);
+        uint32_t d = img[i];
+        double sg;
+        if (hot & (1u << k)) {
+            d = median_dn(img, y, x, c, p.H, p.W, C, p.K);
+            sg = median_std(p.std[k], img, p.std_lut, y, x, c, p.H, p.W, C, p.K);
+        } else {
+            sg = p.std[k] ? p.std[k][i] : p.std_lut[(int64_t)d * C + c];
+        }
+        double w, dw;
+        gaussian_weight(__ddiv_rn((double)d, p.max_dn), w, dw);
+        const double p1 = w * p.lut[(int64_t)d * C + c];
+        merge_accumulate(w, p1, p.dlut[(int64_t)d * C + c], kappa_of(d, p.kappa_scale), sg, rS, p.inv_t[k],
+                         av, as);
+    }
+    double ov = av * rS, os = sqrt(as) * rS;
+    if (p.flat_bytes)
+        flat_epilogue(ov, os, flat_value(p.flat, p.flat_bytes, i, p.max_dn), p.flat_std[i], p.flat_means[c],
+                      p.flat_means[C + c]);
+    p.out_val[i] = ov;
+    p.out_std[i] = os;
+}
+
+__global__ void __launch_bounds__(128)
+merge_fixup_kernel(const __grid_constant__ MergeParams p) {
+    const uint32_t count = p.hot_list[0];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (count <= p.hot_cap) {
+        for (int64_t t = tid; t < count; t += stride)
+            recompute_sample<uint8_t>(p, (int64_t)p.hot_list[kHotListHeader + t]);
+        return;
+    }
+    // the list overflowed (pathological: most of the image is "bad"): rescan every sample
+    const int64_t n = (int64_t)p.H * p.W * p.C;
+    for (int64_t i = tid; i < n; i += stride) {
+        bool any = false;
+        for (int k = 0; k < p.n && !any; ++k)
+            any = p.dark[k] && reinterpret_cast<const uint8_t*>(p.dark[k])[i] >= p.hot_dn[k];
+        if (any) recompute_sample<uint8_t>(p, i);
+    }
+}
+
 // ---- ROI means ------------------------------------------------------------------------------------
 constexpr int kRoiThreads = 256;
 
@@ -342,14 +445,40 @@ int launch_merge_generic_range(const MergeParams& p, int64_t first_item, cudaStr
     return launch_generic<uint8_t>(p, true, first_item, stream);
 }
 
+int launch_dark_scan(const MergeParams& p, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(p.hot_list, 0, kHotListHeader * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return cuda_status(e);
+    dark_scan_kernel<<<sm_count() * 8, 256, 0, stream>>>(p);
+    return launched();
+}
+
+int launch_merge_fixup(const MergeParams& p, cudaStream_t stream) {
+    merge_fixup_kernel<<<sm_count() * 8, 128, 0, stream>>>(p);
+    return launched();
+}
+
+size_t hot_list_entries(int64_t n_samples) {
+    int64_t cap = n_samples / 16;
+    if (cap < 65536) cap = 65536;
+    return (size_t)cap;
+}
+
 }  // namespace cl
 
 extern "C" {
 
 size_t cl_hdr_merge_workspace_bytes(const cl_hdr_merge_args* a) {
     if (!a) return 0;
-    if (a->bits > 256) return cl::table_bytes(a->bits, a->channels);
-    return 0;
+    size_t bytes = 0;
+    if (a->bits > 256) bytes += cl::table_bytes(a->bits, a->channels);
+    // bad-pixel work list of the staged kernel (uint8, 3 channels, dark frames present)
+    bool any_dark = false;
+    if (a->dark)
+        for (int k = 0; k < a->n_exposures && k < CL_MAX_EXPOSURES; ++k) any_dark |= a->dark[k] != nullptr;
+    if (any_dark && a->dn_bytes == 1 && a->channels == 3 && a->algo != 1)
+        bytes += (cl::kHotListHeader + cl::hot_list_entries((int64_t)a->height * a->width * a->channels)) *
+                 sizeof(uint32_t);
+    return bytes;
 }
 
 int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_bytes, void* stream) {
@@ -426,6 +555,17 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
         p.g_pb = pb;
     }
 
+    if (p.any_dark && a->dn_bytes == 1 && p.C == 3 && a->algo != 1) {
+        const size_t off = tab_smem ? 0 : table_bytes(p.bits, p.C);
+        const size_t entries = hot_list_entries((int64_t)p.H * p.W * p.C);
+        if (workspace && aligned(workspace, 16) &&
+            workspace_bytes >= off + (kHotListHeader + entries) * sizeof(uint32_t)) {
+            p.hot_list = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + off);
+            p.hot_cap = (uint32_t)entries;
+        } else if (a->algo == 2) {
+            return CL_ERR_WORKSPACE;
+        }
+    }
     int algo = a->algo;
     const bool staged_ok = merge_staged_supported(p, all_std);
     if (algo == 0) algo = staged_ok ? 2 : 1;

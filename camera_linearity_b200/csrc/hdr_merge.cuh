@@ -30,7 +30,14 @@ struct MergeParams {
     // tables in global memory (16-bit path): wt[bits], pb[bits][C] = {w*g, dlut}
     const double* g_wt;
     const double2* g_pb;
+    // bad-pixel work list of the staged path (see hdr_merge_staged.cu): sample indices whose dark
+    // frame exceeds the threshold in at least one exposure; hot_list[0] is the counter
+    uint32_t* hot_list;
+    uint32_t hot_cap;
+    int32_t reserved;
 };
+
+constexpr size_t kHotListHeader = 4;   // uint32 entries reserved in front of the list (counter + pad)
 
 // One exposure's contribution for one sample.  With S = sum of weights and rS = 1/S:
 //   val = rS * sum_k (w g) / t_k                                   exposure_series.py:388
@@ -113,5 +120,9 @@ __device__ __forceinline__ double flat_value(const void* flat, int flat_bytes, i
 
 int launch_merge_staged(const MergeParams& p, cudaStream_t stream);   // hdr_merge_staged.cu
 bool merge_staged_supported(const MergeParams& p, bool all_std_images);
+// hdr_merge.cu
+int launch_merge_generic_range(const MergeParams& p, int64_t first_item, cudaStream_t stream);
+int launch_dark_scan(const MergeParams& p, cudaStream_t stream);
+int launch_merge_fixup(const MergeParams& p, cudaStream_t stream);
 
 }  // namespace cl

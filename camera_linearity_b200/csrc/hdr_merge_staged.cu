@@ -4,17 +4,23 @@
 //   * producer warp 0 streams the float64 uncertainty images through a ring of shared-memory
 //     stages with cp.async.bulk (the TMA engine's 1-D bulk copy, SASS UBLKCP) and mbarrier
 //     transaction counts -- one 12 KB chunk per (tile, exposure);
-//   * producer warp 1 bulk-copies the DN (and dark-frame) bytes of ALL exposures of the next
-//     tile into the "A buffer" while the consumers are still in pass B of the current tile;
+//   * producer warp 1 bulk-copies the DN bytes of ALL exposures of the next tile into the
+//     "A buffer" while the consumers are still in pass B of the current tile;
 //   * consumer thread t owns pixel t of the 512-pixel tile (3 interleaved samples).  Pass A sums
-//     the Gaussian weights from the A buffer and packs the (median-repaired) DNs into one
-//     register per exposure; pass B consumes one ring stage per exposure.
+//     the Gaussian weights from the A buffer and packs the DNs into one register per exposure;
+//     pass B consumes one ring stage per exposure.
+// Bad pixels (dark frame above threshold, ~0.1 % of the samples) are NOT handled in this kernel:
+// a median gather inside the streaming loop stalls the whole CTA through the ring (measured: 37 us
+// per tile instead of 5).  Instead `dark_scan_kernel` streams the dark frames once and appends the
+// affected sample indices to a work list, this kernel merges every sample as if it were clean, and
+// `merge_fixup_kernel` recomputes the listed samples (median-repaired) and overwrites them.
 // Shared-memory tables are replicated per lane so that the random, DN-indexed gathers are bank-
 // conflict free: w[dn] as 16 copies of a double (LDS.64: half-warp lanes hit 16 distinct bank
 // pairs), {w*g, dICRF}[c][dn] as 8 copies of a double2 (LDS.128: quarter-warp lanes hit 8
 // distinct bank quads).  Without the replication a random 8-bit gather costs ~3 wavefronts per
 // half-warp and the kernel is shared-memory bound well below the HBM roofline.
-// Every input byte crosses HBM once: 9 B per sample-exposure (+1 with a dark frame), 16 B out.
+// Every input byte crosses HBM once: 9 B per sample-exposure (+1 with a dark frame), 16 B out
+// (+ ~1.5 KB of scattered re-reads per bad sample in the fix-up).
 #include "hdr_merge.cuh"
 
 namespace cl {
@@ -33,7 +39,7 @@ constexpr size_t kSmemLimit = 227 * 1024;
 
 struct StagedLayout {
     int stages;
-    uint32_t off_lutA, off_lutB, off_abuf_dn, off_abuf_dark, off_ring, off_bars, total;
+    uint32_t off_lutA, off_lutB, off_abuf_dn, off_ring, off_bars, total;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -78,6 +84,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
+// Releasing a shared-memory stage right after ISSUING the loads that read it is not enough: with
+// 16 warps woken by the same bulk-copy completion the LSU queue can hold the loads for longer than
+// the refill takes to arrive, and the refill then overtakes in-flight reads (seen at a ~1e-4 rate
+// on full-size stacks, never on small ones).  The release is therefore predicated on a value
+// computed FROM the loaded data -- always true (sums of weights / squares are never < 0, and a NaN
+// compares false), but the compiler cannot prove it, so the mbarrier arrive is ordered after the
+// arithmetic that consumed the loads and the scoreboard guarantees they have returned.
+__device__ __forceinline__ bool consumed(double a, double b, double c) { return !((a + b) + c < 0.0); }
+
 template <int NMAX>
 __global__ void __launch_bounds__(kThreads, 1)
 merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L, const int n_tiles) {
@@ -85,7 +100,6 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
     double* lutA = reinterpret_cast<double*>(smem + L.off_lutA);
     double2* lutB = reinterpret_cast<double2*>(smem + L.off_lutB);
     uint8_t* abuf_dn = smem + L.off_abuf_dn;
-    uint8_t* abuf_dark = smem + L.off_abuf_dark;
     unsigned char* ring = smem + L.off_ring;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
     uint64_t* full = bars;                    // [stages]  producer -> consumers (tx bytes)
@@ -138,22 +152,16 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             }
         }
     } else if (warp == kConsumerWarps + 1) {
-        // ===== A-buffer producer: DN (+ dark) bytes of every exposure of one tile =====
+        // ===== A-buffer producer: DN bytes of every exposure of one tile =====
         if (lane == 0) {
             uint32_t ti = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
                 const size_t off = (size_t)tile * kDnChunk;
                 mbar_wait(a_empty, (ti & 1) ^ 1);
-                uint32_t bytes = 0;
-                for (int k = 0; k < p.n; ++k) bytes += kDnChunk + (p.dark[k] ? kDnChunk : 0);
-                mbar_expect_tx(a_full, bytes);
-                for (int k = 0; k < p.n; ++k) {
+                mbar_expect_tx(a_full, (uint32_t)p.n * kDnChunk);
+                for (int k = 0; k < p.n; ++k)
                     bulk_g2s(abuf_dn + k * kDnChunk, reinterpret_cast<const uint8_t*>(p.dn[k]) + off,
                              kDnChunk, a_full);
-                    if (p.dark[k])
-                        bulk_g2s(abuf_dark + k * kDnChunk,
-                                 reinterpret_cast<const uint8_t*>(p.dark[k]) + off, kDnChunk, a_full);
-                }
             }
         }
     } else {
@@ -163,9 +171,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
         uint32_t it = 0, ti = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
             const int64_t px = (int64_t)tile * kTilePx + tid;
-            const int y = (int)(px / p.W), x = (int)(px - (int64_t)y * p.W);
-
-            // ---- pass A: sum of weights; pack DNs + bad-pixel flags into registers ----
+            // ---- pass A: sum of weights; pack the DNs of every exposure into registers ----
             mbar_wait(a_full, ti & 1);
             uint32_t pk[NMAX];
             double S0 = 0.0, S1 = 0.0, S2 = 0.0;
@@ -173,22 +179,16 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             for (int k = 0; k < NMAX; ++k) {
                 if (k < p.n) {
                     const uint8_t* a = abuf_dn + k * kDnChunk + tid * kC;
-                    uint32_t d0 = a[0], d1 = a[1], d2 = a[2], hot = 0;
-                    if (p.dark[k]) {
-                        const uint8_t* b = abuf_dark + k * kDnChunk + tid * kC;
-                        const uint8_t* img = reinterpret_cast<const uint8_t*>(p.dn[k]);
-                        if (b[0] >= p.hot_dn[k]) { hot |= 1; d0 = median_dn(img, y, x, 0, p.H, p.W, kC, p.K); }
-                        if (b[1] >= p.hot_dn[k]) { hot |= 2; d1 = median_dn(img, y, x, 1, p.H, p.W, kC, p.K); }
-                        if (b[2] >= p.hot_dn[k]) { hot |= 4; d2 = median_dn(img, y, x, 2, p.H, p.W, kC, p.K); }
-                    }
+                    const uint32_t d0 = a[0], d1 = a[1], d2 = a[2];
                     S0 += myA[d0 * kLutACopies];
                     S1 += myA[d1 * kLutACopies];
                     S2 += myA[d2 * kLutACopies];
-                    pk[k] = d0 | (d1 << 8) | (d2 << 16) | (hot << 24);
+                    pk[k] = d0 | (d1 << 8) | (d2 << 16);
                 }
             }
+            // release the A buffer; consumed(S) ties the release to the arithmetic that used its bytes
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_empty);
+            if (lane == 0 && consumed(S0, S1, S2)) mbar_arrive(a_empty);
             const double r0 = 1.0 / S0, r1 = 1.0 / S1, r2 = 1.0 / S2;
 
             // ---- pass B: one ring stage per exposure ----
@@ -199,18 +199,9 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
                     const int s = it % stages;
                     mbar_wait(&full[s], (it / stages) & 1);
                     const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
-                    double g0 = sp[0], g1 = sp[1], g2 = sp[2];
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[s]);
-                    ++it;
+                    const double g0 = sp[0], g1 = sp[1], g2 = sp[2];
                     const uint32_t q = pk[k];
-                    const uint32_t d0 = q & 0xFF, d1 = (q >> 8) & 0xFF, d2 = (q >> 16) & 0xFF;
-                    if (q >> 24) {
-                        const uint8_t* img = reinterpret_cast<const uint8_t*>(p.dn[k]);
-                        if (q & (1u << 24)) g0 = median_std(p.std[k], img, p.std_lut, y, x, 0, p.H, p.W, kC, p.K);
-                        if (q & (2u << 24)) g1 = median_std(p.std[k], img, p.std_lut, y, x, 1, p.H, p.W, kC, p.K);
-                        if (q & (4u << 24)) g2 = median_std(p.std[k], img, p.std_lut, y, x, 2, p.H, p.W, kC, p.K);
-                    }
+                    const uint32_t d0 = q & 0xFF, d1 = (q >> 8) & 0xFF, d2 = q >> 16;
                     const double rt = p.inv_t[k];
                     const double w0 = myA[d0 * kLutACopies], w1 = myA[d1 * kLutACopies], w2 = myA[d2 * kLutACopies];
                     const double2 e0 = myB[(0 * 256 + d0) * kLutBCopies];
@@ -219,6 +210,9 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
                     merge_accumulate(w0, e0.x, e0.y, kappa_of(d0, p.kappa_scale), g0, r0, rt, av0, as0);
                     merge_accumulate(w1, e1.x, e1.y, kappa_of(d1, p.kappa_scale), g1, r1, rt, av1, as1);
                     merge_accumulate(w2, e2.x, e2.y, kappa_of(d2, p.kappa_scale), g2, r2, rt, av2, as2);
+                    __syncwarp();
+                    if (lane == 0 && consumed(as0, as1, as2)) mbar_arrive(&empty[s]);
+                    ++it;
                 }
             }
 
@@ -230,15 +224,15 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
                 mbar_wait(&full[s], (it / stages) & 1);
                 const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
                 const double f0 = sp[0], f1 = sp[1], f2 = sp[2];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
-                ++it;
                 flat_epilogue(v0, u0, flat_value(p.flat, p.flat_bytes, i0 + 0, p.max_dn), f0,
                               p.flat_means[0], p.flat_means[kC + 0]);
                 flat_epilogue(v1, u1, flat_value(p.flat, p.flat_bytes, i0 + 1, p.max_dn), f1,
                               p.flat_means[1], p.flat_means[kC + 1]);
                 flat_epilogue(v2, u2, flat_value(p.flat, p.flat_bytes, i0 + 2, p.max_dn), f2,
                               p.flat_means[2], p.flat_means[kC + 2]);
+                __syncwarp();
+                if (lane == 0 && consumed(u0, u1, u2)) mbar_arrive(&empty[s]);
+                ++it;
             }
             p.out_val[i0 + 0] = v0; p.out_val[i0 + 1] = v1; p.out_val[i0 + 2] = v2;
             p.out_std[i0 + 0] = u0; p.out_std[i0 + 1] = u1; p.out_std[i0 + 2] = u2;
@@ -251,7 +245,6 @@ bool make_layout(const MergeParams& p, StagedLayout& L) {
     L.off_lutA = off; off += 256 * kLutACopies * 8;
     L.off_lutB = off; off += kC * 256 * kLutBCopies * 16;
     L.off_abuf_dn = off; off += (uint32_t)p.n * kDnChunk;
-    L.off_abuf_dark = off; if (p.any_dark) off += (uint32_t)p.n * kDnChunk;
     off = (off + 127) & ~127u;
     L.off_ring = off;
     const size_t room = kSmemLimit - 256 - off;
@@ -268,14 +261,12 @@ bool make_layout(const MergeParams& p, StagedLayout& L) {
 
 bool merge_staged_supported(const MergeParams& p, bool all_std_images) {
     if (p.C != kC || p.bits != 256 || p.max_dn != 255.0 || !all_std_images) return false;
-    if ((int64_t)p.H * p.W < kTilePx) return false;
+    if ((int64_t)p.H * p.W < kTilePx || (int64_t)p.H * p.W * kC >= 0xFFFFFFFFll) return false;
+    if (p.any_dark && (!p.hot_list || p.hot_cap == 0)) return false;
     if (p.flat_bytes && !aligned(p.flat_std, 16)) return false;
     StagedLayout L;
     return make_layout(p, L);
 }
-
-// generic kernel on the ragged tail (hdr_merge.cu)
-int launch_merge_generic_range(const MergeParams& p, int64_t first_item, cudaStream_t stream);
 
 int launch_merge_staged(const MergeParams& p, cudaStream_t stream) {
     StagedLayout L;
@@ -292,6 +283,10 @@ int launch_merge_staged(const MergeParams& p, cudaStream_t stream) {
         return launched();
     };
     int st;
+    if (p.any_dark) {                 // work list of bad samples for the fix-up pass
+        st = launch_dark_scan(p, stream);
+        if (st != CL_OK) return st;
+    }
     if (p.n <= 8) st = launch(merge_staged_kernel<8>);
     else if (p.n <= 16) st = launch(merge_staged_kernel<16>);
     else st = launch(merge_staged_kernel<32>);
@@ -299,8 +294,11 @@ int launch_merge_staged(const MergeParams& p, cudaStream_t stream) {
     // pixels past the last full tile (< 512) go through the generic kernel; both kernels run
     // identical arithmetic, so the seam is invisible
     const int64_t tail_first_sample = (int64_t)n_tiles * kTilePx * kC;
-    if (tail_first_sample < n_px * kC) return launch_merge_generic_range(p, tail_first_sample / 4, stream);
-    return CL_OK;
+    if (tail_first_sample < n_px * kC) {
+        st = launch_merge_generic_range(p, tail_first_sample / 4, stream);
+        if (st != CL_OK) return st;
+    }
+    return p.any_dark ? launch_merge_fixup(p, stream) : CL_OK;
 }
 
 }  // namespace cl

@@ -1,9 +1,9 @@
 // K1: ICRF linearisation (LUT gather + derivative for uncertainty propagation).
 // Replaces measurand.py:471-541 of the reference (see include/camera_linearity.h).
 //
-// HBM-bound streaming kernel: each thread owns VEC consecutive samples, loaded with one
-// 16/8-byte vector load (uint8 x16, uint16 x8, f64 x2), the per-channel LUTs live in shared
-// memory ([bits][C] doubles, 12 KB for 8-bit RGB) and outputs are written as 16-byte vectors.
+// HBM-bound streaming kernel: each thread owns 8 strided PAIRS of samples so that every warp-level
+// load and store is contiguous (512 B of float64 per instruction), the per-channel LUTs live in
+// shared memory ([bits][C] doubles, 12 KB for 8-bit RGB) and outputs are written as 16-byte vectors.
 // Algorithmic bytes per sample: b_dn + 8 (out) [+ 8 std in + 8 std out].
 #include "common.cuh"
 
@@ -15,30 +15,35 @@ namespace {
 
 constexpr int kThreads = 256;
 
-template <typename T, int VEC>
-struct alignas(sizeof(T) * VEC) Pack {
-    T v[VEC];
-};
-
 // SRC: 0 = uint8 DN, 1 = uint16 DN, 2 = float64 value in [0, 1]
 template <int SRC>
 struct Src;
 template <>
 struct Src<0> {
     using T = uint8_t;
-    static constexpr int VEC = 16;
+    using Pair = uchar2;
 };
 template <>
 struct Src<1> {
     using T = uint16_t;
-    static constexpr int VEC = 8;
+    using Pair = ushort2;
 };
 template <>
 struct Src<2> {
     using T = double;
-    static constexpr int VEC = 2;
+    using Pair = double2;
 };
 
+constexpr int kSlots = 4;   // pairs of samples per thread; slot u of thread t = pair (u*blockDim + t)
+
+template <int SRC>
+__device__ __forceinline__ uint32_t bin_of(typename Src<SRC>::T v, double max_dn, uint32_t wrap_mask) {
+    if (SRC == 2) return wrap_bin(__dmul_rn((double)v, max_dn), wrap_mask);
+    return (uint32_t)v;
+}
+
+// Every warp-level access is contiguous: in slot u the 32 lanes read 32 consecutive sample PAIRS
+// (64 B of uint8, 512 B of float64) and write 512 B -- fully coalesced loads and stores.
 template <int SRC, bool LUT_SMEM>
 __global__ void __launch_bounds__(kThreads)
 linearize_kernel(const typename Src<SRC>::T* __restrict__ src, double max_dn, uint32_t wrap_mask,
@@ -47,7 +52,7 @@ linearize_kernel(const typename Src<SRC>::T* __restrict__ src, double max_dn, ui
                  double* __restrict__ out_std, uint16_t* __restrict__ bin_out, int64_t n, int C,
                  int bits) {
     using T = typename Src<SRC>::T;
-    constexpr int VEC = Src<SRC>::VEC;
+    using Pair = typename Src<SRC>::Pair;
     extern __shared__ double smem[];
     const double* tv = lut;
     const double* td = dlut;
@@ -62,61 +67,42 @@ linearize_kernel(const typename Src<SRC>::T* __restrict__ src, double max_dn, ui
         td = smem + rows;
     }
     const bool use_std = (std_in != nullptr) && (dlut != nullptr) && (out_std != nullptr);
-    const int64_t n_vec = n / VEC;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += stride) {
-        const int64_t base = v * VEC;
-        const Pack<T, VEC> in = *reinterpret_cast<const Pack<T, VEC>*>(src + base);
-        int c = (int)(base % C);
-        uint32_t bin[VEC];
+    const int64_t n_pairs = n / 2;
+    const int64_t per_block = (int64_t)kSlots * blockDim.x;
+    const int64_t n_blocks_work = (n_pairs + per_block - 1) / per_block;
+    for (int64_t b = blockIdx.x; b < n_blocks_work; b += gridDim.x) {
+        const int64_t first = b * per_block + threadIdx.x;
+        Pair in[kSlots];
+        double2 sd[kSlots];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            if (SRC == 2)
-                bin[j] = wrap_bin(__dmul_rn((double)in.v[j], max_dn), wrap_mask);
-            else
-                bin[j] = (uint32_t)in.v[j];
-        }
-        double ov[VEC], os[VEC];
-        Pack<double, 2> sd[VEC / 2];
-        if (use_std) {
-#pragma unroll
-            for (int j = 0; j < VEC / 2; ++j)
-                sd[j] = *reinterpret_cast<const Pack<double, 2>*>(std_in + base + 2 * j);
-        }
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const int idx = (int)bin[j] * C + c;
-            ov[j] = tv[idx];
-            if (use_std) os[j] = __dmul_rn(td[idx], sd[j / 2].v[j & 1]);
-            c = (c + 1 == C) ? 0 : c + 1;
-        }
-#pragma unroll
-        for (int j = 0; j < VEC / 2; ++j) {
-            Pack<double, 2> o;
-            o.v[0] = ov[2 * j];
-            o.v[1] = ov[2 * j + 1];
-            *reinterpret_cast<Pack<double, 2>*>(out_val + base + 2 * j) = o;
-            if (use_std) {
-                o.v[0] = os[2 * j];
-                o.v[1] = os[2 * j + 1];
-                *reinterpret_cast<Pack<double, 2>*>(out_std + base + 2 * j) = o;
+        for (int u = 0; u < kSlots; ++u) {
+            const int64_t q = first + (int64_t)u * blockDim.x;
+            if (q < n_pairs) {
+                in[u] = reinterpret_cast<const Pair*>(src)[q];
+                if (use_std) sd[u] = reinterpret_cast<const double2*>(std_in)[q];
             }
         }
-        if (bin_out) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) bin_out[base + j] = (uint16_t)bin[j];
+        for (int u = 0; u < kSlots; ++u) {
+            const int64_t q = first + (int64_t)u * blockDim.x;
+            if (q < n_pairs) {
+                const uint32_t b0 = bin_of<SRC>(in[u].x, max_dn, wrap_mask);
+                const uint32_t b1 = bin_of<SRC>(in[u].y, max_dn, wrap_mask);
+                const int c0 = (int)((2 * q) % C);
+                const int c1 = (c0 + 1 == C) ? 0 : c0 + 1;
+                const int i0 = (int)b0 * C + c0, i1 = (int)b1 * C + c1;
+                reinterpret_cast<double2*>(out_val)[q] = make_double2(tv[i0], tv[i1]);
+                if (use_std)
+                    reinterpret_cast<double2*>(out_std)[q] =
+                        make_double2(__dmul_rn(td[i0], sd[u].x), __dmul_rn(td[i1], sd[u].y));
+                if (bin_out) reinterpret_cast<ushort2*>(bin_out)[q] = make_ushort2((uint16_t)b0, (uint16_t)b1);
+            }
         }
     }
-    // ragged tail (n % VEC samples), one thread each
-    const int64_t tail0 = n_vec * VEC;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid < n - tail0) {
-        const int64_t i = tail0 + gid;
-        uint32_t b;
-        if (SRC == 2)
-            b = wrap_bin(__dmul_rn((double)src[i], max_dn), wrap_mask);
-        else
-            b = (uint32_t)src[i];
+    // odd tail sample
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        const uint32_t b = bin_of<SRC>(src[i], max_dn, wrap_mask);
         const int idx = (int)b * C + (int)(i % C);
         out_val[i] = tv[idx];
         if (use_std) out_std[i] = __dmul_rn(td[idx], std_in[i]);
@@ -129,16 +115,15 @@ int launch(const void* src, double max_dn, const double* std_in, const double* l
            const double* dlut, double* out_val, double* out_std, uint16_t* bin_out, int64_t n,
            int C, int bits, uint32_t wrap_mask, cudaStream_t stream) {
     using T = typename Src<SRC>::T;
-    constexpr int VEC = Src<SRC>::VEC;
     if (n == 0) return CL_OK;
-    // vector accesses need the natural alignment of the vectors
-    if (!aligned(src, sizeof(T) * VEC) || !aligned(out_val, 16) ||
-        (std_in && !aligned(std_in, 16)) || (out_std && !aligned(out_std, 16)))
+    // pair accesses need the natural alignment of a pair
+    if (!aligned(src, sizeof(T) * 2) || !aligned(out_val, 16) || (std_in && !aligned(std_in, 16)) ||
+        (out_std && !aligned(out_std, 16)) || (bin_out && !aligned(bin_out, 4)))
         return CL_ERR_ALIGNMENT;
     const size_t lut_bytes = (size_t)bits * C * sizeof(double) * 2;
     const bool lut_smem = lut_bytes <= 96 * 1024;
-    const int64_t n_vec = (n + VEC - 1) / VEC;
-    int64_t blocks = (n_vec + kThreads - 1) / kThreads;
+    const int64_t per_block = (int64_t)kSlots * kThreads;
+    int64_t blocks = (n / 2 + per_block - 1) / per_block;
     const int64_t cap = (int64_t)sm_count() * 8;  // 8 resident CTAs of 256 threads per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;

@@ -11,7 +11,15 @@ from camera_linearity_b200 import ExposureSeries, GlobalSettings, ImageSet, Meas
 from camera_linearity_b200.image_set import _features_from_file_name
 from oracle import hdr_merge as om
 
-GlobalSettings.DEVICE = "cpu"
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _cpu_tensors():
+    """Host-logic tests run on CPU tensors; restore the default device afterwards."""
+    previous = GlobalSettings.DEVICE
+    GlobalSettings.DEVICE = "cpu"
+    yield
+    GlobalSettings.DEVICE = previous
 
 
 def test_image_set_defaults():

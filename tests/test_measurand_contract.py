@@ -12,7 +12,15 @@ from hypothesis import strategies as st
 from camera_linearity_b200 import Measurand, AbstractMeasurand, GlobalSettings
 from camera_linearity_b200 import general_functions as gf
 
-GlobalSettings.DEVICE = "cpu"
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _cpu_tensors():
+    """Host-logic tests run on CPU tensors; restore the default device afterwards."""
+    previous = GlobalSettings.DEVICE
+    GlobalSettings.DEVICE = "cpu"
+    yield
+    GlobalSettings.DEVICE = previous
 
 
 @st.composite
