@@ -224,38 +224,74 @@ int launch_generic(const MergeParams& p, bool tab_smem, int64_t first_item, cuda
 
 // ---- bad-pixel work list (staged path) ------------------------------------------------------------
 // Streams the dark frames once (16 bytes per thread per load, SIMD byte compare) and appends the
-// index of every sample whose dark DN reaches the exposure's integer threshold.
-__device__ __forceinline__ void hot_append(const MergeParams& p, uint32_t sample) {
-    const uint32_t slot = atomicAdd(&p.hot_list[0], 1u);
-    if (slot < p.hot_cap) p.hot_list[kHotListHeader + slot] = sample;
-}
+// index of every sample whose dark DN reaches the exposure's integer threshold.  Hits are staged
+// in a per-CTA shared-memory list and flushed with ONE global atomic per flush: ~10^5 returning
+// atomics on a single counter would serialise in L2 and cost more than the merge itself.
+constexpr int kScanThreads = 256;
+constexpr int kScanLocal = 2048;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kScanThreads)
 dark_scan_kernel(const __grid_constant__ MergeParams p) {
+    __shared__ uint32_t s_list[kScanLocal];
+    __shared__ uint32_t s_count, s_base;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
     const int64_t n = (int64_t)p.H * p.W * p.C;
-    const int64_t n_vec = n / 16;
+    const int64_t n_vec = (n + 15) / 16;                 // the last vector may be ragged
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+
+    auto flush = [&]() {                                 // block-uniform call sites only
+        __syncthreads();
+        const uint32_t cnt = s_count < kScanLocal ? s_count : kScanLocal;
+        if (threadIdx.x == 0) s_base = atomicAdd(&p.hot_list[0], cnt);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+            if (s_base + i < p.hot_cap) p.hot_list[kHotListHeader + s_base + i] = s_list[i];
+        __syncthreads();
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+    };
+    auto hit = [&](uint32_t sample) {
+        const uint32_t slot = atomicAdd(&s_count, 1u);
+        if (slot < kScanLocal) {
+            s_list[slot] = sample;
+        } else {                                          // dense bad region: straight to the global list
+            const uint32_t g = atomicAdd(&p.hot_list[0], 1u);
+            if (g < p.hot_cap) p.hot_list[kHotListHeader + g] = sample;
+        }
+    };
+
     for (int k = 0; k < p.n; ++k) {
         if (!p.dark[k] || p.hot_dn[k] > 255u) continue;
         const uint32_t thr = p.hot_dn[k] * 0x01010101u;
-        const uint4* src = reinterpret_cast<const uint4*>(p.dark[k]);
-        for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += stride) {
-            const uint4 q = __ldg(src + v);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(p.dark[k]);
+        for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_vec; base += stride) {
+            const int64_t v = base + threadIdx.x;
+            if (v < n_vec) {
+                if (v * 16 + 16 <= n) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(bytes) + v);
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint32_t m = __vcmpgeu4(w[j], thr);
-                while (m) {
-                    const int b = (__ffs(m) - 1) >> 3;
-                    hot_append(p, (uint32_t)(v * 16 + j * 4 + b));
-                    m &= ~(0xFFu << (8 * b));
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t m = __vcmpgeu4(w[j], thr);
+                        while (m) {
+                            const int b = (__ffs(m) - 1) >> 3;
+                            hit((uint32_t)(v * 16 + j * 4 + b));
+                            m &= ~(0xFFu << (8 * b));
+                        }
+                    }
+                } else {
+                    for (int64_t i = v * 16; i < n; ++i)
+                        if (bytes[i] >= p.hot_dn[k]) hit((uint32_t)i);
                 }
             }
+            __syncthreads();
+            const uint32_t pending = s_count;            // read between two barriers: block-uniform
+            __syncthreads();
+            if (pending >= kScanLocal / 4) flush();
         }
-        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(p.dark[k]);
-        for (int64_t i = n_vec * 16 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-            if (bytes[i] >= p.hot_dn[k]) hot_append(p, (uint32_t)i);
     }
+    flush();
 }
 
 // Full recomputation of one sample with the bad-pixel repair, same arithmetic (and the same
@@ -448,7 +484,7 @@ int launch_merge_generic_range(const MergeParams& p, int64_t first_item, cudaStr
 int launch_dark_scan(const MergeParams& p, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(p.hot_list, 0, kHotListHeader * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return cuda_status(e);
-    dark_scan_kernel<<<sm_count() * 8, 256, 0, stream>>>(p);
+    dark_scan_kernel<<<sm_count() * 4, kScanThreads, 0, stream>>>(p);
     return launched();
 }
 

@@ -111,6 +111,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
     const int warp = tid >> 5, lane = tid & 31;
     const int stages = L.stages;
     const bool has_flat = p.flat_bytes != 0;
+    const bool flat_u8 = p.flat_bytes == 1;     // flat DN bytes ride in the A buffer (slot n)
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -138,16 +139,17 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
     if (warp == kConsumerWarps) {
         // ===== ring producer: std chunks (tile-major, exposure-minor; flat std last) =====
         if (lane == 0) {
-            uint32_t it = 0;
+            int s = 0;
+            uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const size_t off = (size_t)tile * kTilePx * kC;   // first sample of the tile
                 const int chunks = p.n + (has_flat ? 1 : 0);
-                for (int k = 0; k < chunks; ++k, ++it) {
-                    const int s = it % stages;
-                    mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+                for (int k = 0; k < chunks; ++k) {
+                    mbar_wait(&empty[s], phase ^ 1);
                     mbar_expect_tx(&full[s], kStdChunk);
                     const double* src = (k < p.n ? p.std[k] : p.flat_std) + off;
                     bulk_g2s(ring + (size_t)s * kStdChunk, src, kStdChunk, &full[s]);
+                    if (++s == stages) { s = 0; phase ^= 1; }
                 }
             }
         }
@@ -158,9 +160,12 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
                 const size_t off = (size_t)tile * kDnChunk;
                 mbar_wait(a_empty, (ti & 1) ^ 1);
-                mbar_expect_tx(a_full, (uint32_t)p.n * kDnChunk);
+                mbar_expect_tx(a_full, (uint32_t)(p.n + (flat_u8 ? 1 : 0)) * kDnChunk);
                 for (int k = 0; k < p.n; ++k)
                     bulk_g2s(abuf_dn + k * kDnChunk, reinterpret_cast<const uint8_t*>(p.dn[k]) + off,
+                             kDnChunk, a_full);
+                if (flat_u8)
+                    bulk_g2s(abuf_dn + p.n * kDnChunk, reinterpret_cast<const uint8_t*>(p.flat) + off,
                              kDnChunk, a_full);
             }
         }
@@ -168,7 +173,8 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
         // ===== consumers: thread tid owns pixel tid of each tile =====
         const double* myA = lutA + (lane & (kLutACopies - 1));
         const double2* myB = lutB + (lane & (kLutBCopies - 1));
-        uint32_t it = 0, ti = 0;
+        uint32_t ti = 0, phase = 0;
+        int s = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
             const int64_t px = (int64_t)tile * kTilePx + tid;
             // ---- pass A: sum of weights; pack the DNs of every exposure into registers ----
@@ -186,9 +192,14 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
                     pk[k] = d0 | (d1 << 8) | (d2 << 16);
                 }
             }
+            uint32_t pkf = 0;
+            if (flat_u8) {
+                const uint8_t* a = abuf_dn + p.n * kDnChunk + tid * kC;
+                pkf = (uint32_t)a[0] | ((uint32_t)a[1] << 8) | ((uint32_t)a[2] << 16);
+            }
             // release the A buffer; consumed(S) ties the release to the arithmetic that used its bytes
             __syncwarp();
-            if (lane == 0 && consumed(S0, S1, S2)) mbar_arrive(a_empty);
+            if (lane == 0 && consumed(S0, S1, S2 + (double)pkf)) mbar_arrive(a_empty);   // pkf >= 0
             const double r0 = 1.0 / S0, r1 = 1.0 / S1, r2 = 1.0 / S2;
 
             // ---- pass B: one ring stage per exposure ----
@@ -196,8 +207,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
 #pragma unroll
             for (int k = 0; k < NMAX; ++k) {
                 if (k < p.n) {
-                    const int s = it % stages;
-                    mbar_wait(&full[s], (it / stages) & 1);
+                    mbar_wait(&full[s], phase);
                     const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
                     const double g0 = sp[0], g1 = sp[1], g2 = sp[2];
                     const uint32_t q = pk[k];
@@ -212,7 +222,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
                     merge_accumulate(w2, e2.x, e2.y, kappa_of(d2, p.kappa_scale), g2, r2, rt, av2, as2);
                     __syncwarp();
                     if (lane == 0 && consumed(as0, as1, as2)) mbar_arrive(&empty[s]);
-                    ++it;
+                    if (++s == stages) { s = 0; phase ^= 1; }
                 }
             }
 
@@ -220,19 +230,25 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             double u0 = sqrt(as0) * r0, u1 = sqrt(as1) * r1, u2 = sqrt(as2) * r2;
             const int64_t i0 = px * kC;
             if (has_flat) {
-                const int s = it % stages;
-                mbar_wait(&full[s], (it / stages) & 1);
+                mbar_wait(&full[s], phase);
                 const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
                 const double f0 = sp[0], f1 = sp[1], f2 = sp[2];
-                flat_epilogue(v0, u0, flat_value(p.flat, p.flat_bytes, i0 + 0, p.max_dn), f0,
-                              p.flat_means[0], p.flat_means[kC + 0]);
-                flat_epilogue(v1, u1, flat_value(p.flat, p.flat_bytes, i0 + 1, p.max_dn), f1,
-                              p.flat_means[1], p.flat_means[kC + 1]);
-                flat_epilogue(v2, u2, flat_value(p.flat, p.flat_bytes, i0 + 2, p.max_dn), f2,
-                              p.flat_means[2], p.flat_means[kC + 2]);
+                double fv0, fv1, fv2;
+                if (flat_u8) {
+                    fv0 = __ddiv_rn((double)(pkf & 0xFF), p.max_dn);
+                    fv1 = __ddiv_rn((double)((pkf >> 8) & 0xFF), p.max_dn);
+                    fv2 = __ddiv_rn((double)(pkf >> 16), p.max_dn);
+                } else {
+                    fv0 = flat_value(p.flat, p.flat_bytes, i0 + 0, p.max_dn);
+                    fv1 = flat_value(p.flat, p.flat_bytes, i0 + 1, p.max_dn);
+                    fv2 = flat_value(p.flat, p.flat_bytes, i0 + 2, p.max_dn);
+                }
+                flat_epilogue(v0, u0, fv0, f0, p.flat_means[0], p.flat_means[kC + 0]);
+                flat_epilogue(v1, u1, fv1, f1, p.flat_means[1], p.flat_means[kC + 1]);
+                flat_epilogue(v2, u2, fv2, f2, p.flat_means[2], p.flat_means[kC + 2]);
                 __syncwarp();
                 if (lane == 0 && consumed(u0, u1, u2)) mbar_arrive(&empty[s]);
-                ++it;
+                if (++s == stages) { s = 0; phase ^= 1; }
             }
             p.out_val[i0 + 0] = v0; p.out_val[i0 + 1] = v1; p.out_val[i0 + 2] = v2;
             p.out_std[i0 + 0] = u0; p.out_std[i0 + 1] = u1; p.out_std[i0 + 2] = u2;
@@ -244,7 +260,7 @@ bool make_layout(const MergeParams& p, StagedLayout& L) {
     uint32_t off = 0;
     L.off_lutA = off; off += 256 * kLutACopies * 8;
     L.off_lutB = off; off += kC * 256 * kLutBCopies * 16;
-    L.off_abuf_dn = off; off += (uint32_t)p.n * kDnChunk;
+    L.off_abuf_dn = off; off += (uint32_t)(p.n + (p.flat_bytes == 1 ? 1 : 0)) * kDnChunk;
     off = (off + 127) & ~127u;
     L.off_ring = off;
     const size_t room = kSmemLimit - 256 - off;
@@ -263,7 +279,7 @@ bool merge_staged_supported(const MergeParams& p, bool all_std_images) {
     if (p.C != kC || p.bits != 256 || p.max_dn != 255.0 || !all_std_images) return false;
     if ((int64_t)p.H * p.W < kTilePx || (int64_t)p.H * p.W * kC >= 0xFFFFFFFFll) return false;
     if (p.any_dark && (!p.hot_list || p.hot_cap == 0)) return false;
-    if (p.flat_bytes && !aligned(p.flat_std, 16)) return false;
+    if (p.flat_bytes && (!aligned(p.flat_std, 16) || !aligned(p.flat, 16))) return false;
     StagedLayout L;
     return make_layout(p, L);
 }
