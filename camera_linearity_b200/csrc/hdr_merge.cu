@@ -222,76 +222,105 @@ int launch_generic(const MergeParams& p, bool tab_smem, int64_t first_item, cuda
     return launched();
 }
 
-// ---- bad-pixel work list (staged path) ------------------------------------------------------------
-// Streams the dark frames once (16 bytes per thread per load, SIMD byte compare) and appends the
-// index of every sample whose dark DN reaches the exposure's integer threshold.  Hits are staged
-// in a per-CTA shared-memory list and flushed with ONE global atomic per flush: ~10^5 returning
-// atomics on a single counter would serialise in L2 and cost more than the merge itself.
+// ---- bad-pixel patches (staged path) ----------------------------------------------------------------
+// Streams the dark frames once (64 bytes per thread in flight, SIMD byte compare).  For every
+// (sample, exposure) whose dark DN reaches the exposure's integer threshold it computes the K x K
+// medians of the DN and of the uncertainty (the rare, gather-heavy part) and files a patch
+// {pixel-in-tile, channel, exposure, repaired DN, repaired sigma} in the bucket of the 512-pixel
+// tile the sample belongs to.  The streaming merge kernel applies the patches of its current
+// tile from shared memory, so the repair costs it no global gathers.  Samples that do not fit a
+// bucket (more than kBucketCap bad (sample, exposure) pairs in one tile) go to the global
+// fix-up list instead and are recomputed in full by merge_fixup_kernel.
 constexpr int kScanThreads = 256;
-constexpr int kScanLocal = 2048;
+constexpr int kScanVecs = 4;
 
+__device__ __noinline__ void file_patch(const MergeParams& p, int k, uint32_t sample) {
+    const uint32_t px = sample / 3u, c = sample - px * 3u;
+    const uint32_t tile = px / kStagedTilePx;
+    if ((int)tile >= p.n_full_tiles) return;            // ragged tail: the generic kernel repairs inline
+    const int y = (int)(px / (uint32_t)p.W), x = (int)(px - (uint32_t)y * (uint32_t)p.W);
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(p.dn[k]);
+    const uint32_t d_new = median_dn(img, y, x, (int)c, p.H, p.W, 3, p.K);
+    const double s_new = median_std(p.std[k], img, p.std_lut, y, x, (int)c, p.H, p.W, 3, p.K);
+    uint32_t* bucket = p.buckets + (size_t)tile * kBucketWords;
+    const uint32_t slot = atomicAdd(bucket, 1u);
+    if (slot < (uint32_t)kBucketCap) {
+        uint32_t* e = bucket + 4 + 4 * slot;
+        e[0] = (px - tile * kStagedTilePx) | (c << 9) | ((uint32_t)k << 11) | (d_new << 16);
+        *reinterpret_cast<double*>(e + 2) = s_new;
+    } else {
+        const uint32_t g = atomicAdd(&p.hot_list[0], 1u);
+        if (g < p.hot_cap) p.hot_list[kHotListHeader + g] = sample;
+    }
+}
+
+constexpr int kScanLocal = 1024;
+
+// Two phases per block iteration so that the gather-heavy median work is not serialised inside
+// diverged warps: (1) every thread compares 64 dark bytes and pushes its (rare) hits to a
+// shared-memory list, (2) the CTA drains the list with one hit per thread.
 __global__ void __launch_bounds__(kScanThreads)
 dark_scan_kernel(const __grid_constant__ MergeParams p) {
-    __shared__ uint32_t s_list[kScanLocal];
-    __shared__ uint32_t s_count, s_base;
+    __shared__ uint2 s_hits[kScanLocal];        // {sample, exposure}
+    __shared__ uint32_t s_count;
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
     const int64_t n = (int64_t)p.H * p.W * p.C;
-    const int64_t n_vec = (n + 15) / 16;                 // the last vector may be ragged
+    const int64_t n_vec = (n + 15) / 16;        // the last vector may be ragged
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 
-    auto flush = [&]() {                                 // block-uniform call sites only
+    auto hit = [&](int k, uint32_t sample) {
+        const uint32_t slot = atomicAdd(&s_count, 1u);
+        if (slot < kScanLocal) s_hits[slot] = make_uint2(sample, (uint32_t)k);
+        else file_patch(p, k, sample);           // dense bad region: no room, repair right here
+    };
+    auto drain = [&]() {                         // block-uniform call sites only
         __syncthreads();
-        const uint32_t cnt = s_count < kScanLocal ? s_count : kScanLocal;
-        if (threadIdx.x == 0) s_base = atomicAdd(&p.hot_list[0], cnt);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
-            if (s_base + i < p.hot_cap) p.hot_list[kHotListHeader + s_base + i] = s_list[i];
+        const uint32_t cnt = min(s_count, (uint32_t)kScanLocal);
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) file_patch(p, (int)s_hits[i].y, s_hits[i].x);
         __syncthreads();
         if (threadIdx.x == 0) s_count = 0;
         __syncthreads();
-    };
-    auto hit = [&](uint32_t sample) {
-        const uint32_t slot = atomicAdd(&s_count, 1u);
-        if (slot < kScanLocal) {
-            s_list[slot] = sample;
-        } else {                                          // dense bad region: straight to the global list
-            const uint32_t g = atomicAdd(&p.hot_list[0], 1u);
-            if (g < p.hot_cap) p.hot_list[kHotListHeader + g] = sample;
-        }
     };
 
     for (int k = 0; k < p.n; ++k) {
         if (!p.dark[k] || p.hot_dn[k] > 255u) continue;
         const uint32_t thr = p.hot_dn[k] * 0x01010101u;
         const uint8_t* bytes = reinterpret_cast<const uint8_t*>(p.dark[k]);
-        for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_vec; base += stride) {
-            const int64_t v = base + threadIdx.x;
-            if (v < n_vec) {
+        const uint4* src = reinterpret_cast<const uint4*>(bytes);
+        for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_vec; base += stride * kScanVecs) {
+            uint4 q[kScanVecs];
+#pragma unroll
+            for (int u = 0; u < kScanVecs; ++u) {
+                const int64_t v = base + threadIdx.x + u * stride;
+                q[u] = (v * 16 + 16 <= n) ? __ldg(src + v) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < kScanVecs; ++u) {
+                const int64_t v = base + threadIdx.x + u * stride;
                 if (v * 16 + 16 <= n) {
-                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(bytes) + v);
-                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                    const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint32_t m = __vcmpgeu4(w[j], thr);
                         while (m) {
                             const int b = (__ffs(m) - 1) >> 3;
-                            hit((uint32_t)(v * 16 + j * 4 + b));
+                            hit(k, (uint32_t)(v * 16 + j * 4 + b));
                             m &= ~(0xFFu << (8 * b));
                         }
                     }
-                } else {
+                } else if (v < n_vec) {           // ragged last vector
                     for (int64_t i = v * 16; i < n; ++i)
-                        if (bytes[i] >= p.hot_dn[k]) hit((uint32_t)i);
+                        if (bytes[i] >= p.hot_dn[k]) hit(k, (uint32_t)i);
                 }
             }
             __syncthreads();
-            const uint32_t pending = s_count;            // read between two barriers: block-uniform
+            const uint32_t pending = s_count;    // read between two barriers: block-uniform
             __syncthreads();
-            if (pending >= kScanLocal / 4) flush();
+            if (pending >= kScanThreads) drain();
         }
     }
-    flush();
+    drain();
 }
 
 // Full recomputation of one sample with the bad-pixel repair, same arithmetic (and the same
@@ -396,16 +425,18 @@ __global__ void roi_partial_kernel(const void* __restrict__ flat, int flat_bytes
     }
 }
 
+// one warp per output (2C warps): lanes stride over the per-block partials, fixed-order tree
 __global__ void roi_final_kernel(const double* __restrict__ partial, int n_blocks, int C,
                                  double count, double* __restrict__ out) {
-    const int c = threadIdx.x;
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (c >= 2 * C) return;
     double s = 0.0;
-    for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)b * 2 * C + c];
-    out[c] = s / count;
+    for (int b = lane; b < n_blocks; b += 32) s += partial[(int64_t)b * 2 * C + c];
+    s = warp_sum(s);
+    if (lane == 0) out[c] = s / count;
 }
 
-constexpr int kRoiBlocks = 64;
+constexpr int kRoiBlocks = 592;
 
 // ---- stand-alone Measurand kernels ------------------------------------------------------------------
 __global__ void gaussian_weight_kernel(const double* __restrict__ val, double* __restrict__ w,
@@ -484,8 +515,15 @@ int launch_merge_generic_range(const MergeParams& p, int64_t first_item, cudaStr
 int launch_dark_scan(const MergeParams& p, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(p.hot_list, 0, kHotListHeader * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return cuda_status(e);
+    // zero the 16-byte header (count) of every tile bucket
+    e = cudaMemset2DAsync(p.buckets, kBucketWords * sizeof(uint32_t), 0, 16, (size_t)p.n_full_tiles, stream);
+    if (e != cudaSuccess) return cuda_status(e);
     dark_scan_kernel<<<sm_count() * 4, kScanThreads, 0, stream>>>(p);
     return launched();
+}
+
+size_t bucket_bytes(int64_t n_pixels) {
+    return (size_t)(n_pixels / kStagedTilePx) * kBucketWords * sizeof(uint32_t);
 }
 
 int launch_merge_fixup(const MergeParams& p, cudaStream_t stream) {
@@ -513,7 +551,8 @@ size_t cl_hdr_merge_workspace_bytes(const cl_hdr_merge_args* a) {
         for (int k = 0; k < a->n_exposures && k < CL_MAX_EXPOSURES; ++k) any_dark |= a->dark[k] != nullptr;
     if (any_dark && a->dn_bytes == 1 && a->channels == 3 && a->algo != 1)
         bytes += (cl::kHotListHeader + cl::hot_list_entries((int64_t)a->height * a->width * a->channels)) *
-                 sizeof(uint32_t);
+                     sizeof(uint32_t) +
+                 cl::bucket_bytes((int64_t)a->height * a->width) + 16;
     return bytes;
 }
 
@@ -594,10 +633,13 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
     if (p.any_dark && a->dn_bytes == 1 && p.C == 3 && a->algo != 1) {
         const size_t off = tab_smem ? 0 : table_bytes(p.bits, p.C);
         const size_t entries = hot_list_entries((int64_t)p.H * p.W * p.C);
+        const size_t list_bytes = ((kHotListHeader + entries) * sizeof(uint32_t) + 15) / 16 * 16;
         if (workspace && aligned(workspace, 16) &&
-            workspace_bytes >= off + (kHotListHeader + entries) * sizeof(uint32_t)) {
+            workspace_bytes >= off + list_bytes + bucket_bytes((int64_t)p.H * p.W)) {
             p.hot_list = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + off);
             p.hot_cap = (uint32_t)entries;
+            p.buckets = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + off + list_bytes);
+            p.n_full_tiles = (int32_t)(((int64_t)p.H * p.W) / kStagedTilePx);
         } else if (a->algo == 2) {
             return CL_ERR_WORKSPACE;
         }
@@ -641,7 +683,7 @@ int cl_flat_roi_means(const void* flat, int flat_bytes, double max_dn, const dou
                                                          rw > 0 ? rw : 1, partial);
     int st = launched();
     if (st != CL_OK) return st;
-    roi_final_kernel<<<1, 32, 0, s>>>(partial, kRoiBlocks, channels, (double)rh * (double)rw,
+    roi_final_kernel<<<1, 64 * CL_MAX_CHANNELS, 0, s>>>(partial, kRoiBlocks, channels, (double)rh * (double)rw,
                                       out_means);
     return launched();
 }

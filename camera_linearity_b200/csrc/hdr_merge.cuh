@@ -34,10 +34,16 @@ struct MergeParams {
     // frame exceeds the threshold in at least one exposure; hot_list[0] is the counter
     uint32_t* hot_list;
     uint32_t hot_cap;
-    int32_t reserved;
+    int32_t n_full_tiles;      // 512-pixel tiles handled by the staged kernel
+    // per-tile bad-pixel patch buckets (staged path): [count, pad x3][kBucketCap x {meta, pad, sigma}]
+    uint32_t* buckets;
 };
 
 constexpr size_t kHotListHeader = 4;   // uint32 entries reserved in front of the list (counter + pad)
+constexpr int kStagedTilePx = 512;     // pixels per tile of the staged kernel
+constexpr int kBucketCap = 32;         // patch entries per tile; more -> the sample goes to the fix-up list
+constexpr int kBucketWords = 4 + 4 * kBucketCap;   // uint32 words per bucket (528 bytes)
+// entry meta word: pixel-in-tile [0,9) | channel [9,11) | exposure [11,16) | repaired DN [16,24)
 
 // One exposure's contribution for one sample.  With S = sum of weights and rS = 1/S:
 //   val = rS * sum_k (w g) / t_k                                   exposure_series.py:388

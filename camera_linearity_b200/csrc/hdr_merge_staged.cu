@@ -1,6 +1,6 @@
 // K2 fast path ("algo 2"): bulk-copy staged HDR merge for 8-bit, 3-channel stacks on sm_100a.
 //
-// One persistent CTA per SM (grid = #SMs), 16 consumer warps + 2 producer warps:
+// One persistent CTA per SM (grid = #SMs), 16 consumer warps + 2 producer warps + 1 patcher warp:
 //   * producer warp 0 streams the float64 uncertainty images through a ring of shared-memory
 //     stages with cp.async.bulk (the TMA engine's 1-D bulk copy, SASS UBLKCP) and mbarrier
 //     transaction counts -- one 12 KB chunk per (tile, exposure);
@@ -9,11 +9,15 @@
 //   * consumer thread t owns pixel t of the 512-pixel tile (3 interleaved samples).  Pass A sums
 //     the Gaussian weights from the A buffer and packs the DNs into one register per exposure;
 //     pass B consumes one ring stage per exposure.
-// Bad pixels (dark frame above threshold, ~0.1 % of the samples) are NOT handled in this kernel:
+// Bad pixels (dark frame above threshold, ~0.1 % of the samples) cost this kernel no global gathers:
 // a median gather inside the streaming loop stalls the whole CTA through the ring (measured: 37 us
-// per tile instead of 5).  Instead `dark_scan_kernel` streams the dark frames once and appends the
-// affected sample indices to a work list, this kernel merges every sample as if it were clean, and
-// `merge_fixup_kernel` recomputes the listed samples (median-repaired) and overwrites them.
+// per tile instead of 5).  Instead `dark_scan_kernel` streams the dark frames once, computes the
+// repaired DN / sigma of every bad (sample, exposure) and files them in per-tile patch buckets;
+// the A-buffer producer brings the tile's bucket (528 B) into shared memory and a dedicated
+// PATCHER warp writes the repaired values over the staged bytes (DNs in the A buffer, sigmas in the
+// ring stage) before the consumers are told the data is ready -- the consumers' loops carry no
+// patch code at all.  Tiles with more than 32 patches spill to a global list that
+// `merge_fixup_kernel` recomputes in full afterwards.
 // Shared-memory tables are replicated per lane so that the random, DN-indexed gathers are bank-
 // conflict free: w[dn] as 16 copies of a double (LDS.64: half-warp lanes hit 16 distinct bank
 // pairs), {w*g, dICRF}[c][dn] as 8 copies of a double2 (LDS.128: quarter-warp lanes hit 8
@@ -26,10 +30,10 @@
 namespace cl {
 namespace {
 
-constexpr int kTilePx = 512;
+constexpr int kTilePx = kStagedTilePx;
 constexpr int kC = 3;
 constexpr int kConsumerWarps = kTilePx / 32;
-constexpr int kThreads = kTilePx + 64;          // + ring producer warp + A-buffer producer warp
+constexpr int kThreads = kTilePx + 96;          // + ring producer, A-buffer producer and patcher warps
 constexpr int kDnChunk = kTilePx * kC;          // bytes of one exposure's DN tile
 constexpr int kStdChunk = kTilePx * kC * 8;     // bytes of one exposure's std tile
 constexpr int kLutACopies = 16;
@@ -39,7 +43,7 @@ constexpr size_t kSmemLimit = 227 * 1024;
 
 struct StagedLayout {
     int stages;
-    uint32_t off_lutA, off_lutB, off_abuf_dn, off_ring, off_bars, total;
+    uint32_t off_lutA, off_lutB, off_abuf_dn, off_bucket, off_ring, off_bars, total;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -100,12 +104,16 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
     double* lutA = reinterpret_cast<double*>(smem + L.off_lutA);
     double2* lutB = reinterpret_cast<double2*>(smem + L.off_lutB);
     uint8_t* abuf_dn = smem + L.off_abuf_dn;
+    const uint32_t* bucket_s = reinterpret_cast<const uint32_t*>(smem + L.off_bucket);   // [kBucketWords]
+    const bool patched = p.any_dark != 0;
     unsigned char* ring = smem + L.off_ring;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
     uint64_t* full = bars;                    // [stages]  producer -> consumers (tx bytes)
     uint64_t* empty = bars + kMaxStages;      // [stages]  consumers -> producer
-    uint64_t* a_full = bars + 2 * kMaxStages;
+    uint64_t* ready = bars + 2 * kMaxStages;  // [stages]  patcher -> consumers (bad-pixel patches applied)
+    uint64_t* a_full = bars + 3 * kMaxStages;
     uint64_t* a_empty = a_full + 1;
+    uint64_t* a_ready = a_full + 2;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -117,9 +125,11 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kConsumerWarps);
+            mbar_init(&ready[s], 1);
         }
         mbar_init(a_full, 1);
         mbar_init(a_empty, kConsumerWarps);
+        mbar_init(a_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // replicated tables (see file header)
@@ -160,7 +170,11 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
                 const size_t off = (size_t)tile * kDnChunk;
                 mbar_wait(a_empty, (ti & 1) ^ 1);
-                mbar_expect_tx(a_full, (uint32_t)(p.n + (flat_u8 ? 1 : 0)) * kDnChunk);
+                mbar_expect_tx(a_full, (uint32_t)(p.n + (flat_u8 ? 1 : 0)) * kDnChunk +
+                                           (patched ? kBucketWords * 4u : 0u));
+                if (patched)
+                    bulk_g2s(smem + L.off_bucket, p.buckets + (size_t)tile * kBucketWords, kBucketWords * 4,
+                             a_full);
                 for (int k = 0; k < p.n; ++k)
                     bulk_g2s(abuf_dn + k * kDnChunk, reinterpret_cast<const uint8_t*>(p.dn[k]) + off,
                              kDnChunk, a_full);
@@ -169,8 +183,42 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
                              kDnChunk, a_full);
             }
         }
+    } else if (warp == kConsumerWarps + 2) {
+        // ===== patcher: applies the tile's bad-pixel patches to the staged data in shared memory =====
+        // lane e owns bucket entry e.  DN patches go into the A buffer before pass A, sigma patches
+        // into ring stage (tile, k) right after it lands; consumers wait on a_ready / ready[] instead
+        // of a_full / full[], so their loops carry no patch code and stay exact.
+        if (patched) {
+            uint32_t ti = 0, phase = 0;
+            int s = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+                mbar_wait(a_full, ti & 1);
+                const uint32_t n_patch = min(bucket_s[0], (uint32_t)kBucketCap);
+                const bool mine = (uint32_t)lane < n_patch;
+                const uint32_t meta = mine ? bucket_s[4 + 4 * lane] : 0u;
+                const double sig = mine ? *reinterpret_cast<const double*>(bucket_s + 4 + 4 * lane + 2) : 0.0;
+                const uint32_t pos = (meta & 511u) * kC + ((meta >> 9) & 3u);     // sample within the tile
+                const int ke = (int)((meta >> 11) & 31u);
+                if (mine) abuf_dn[ke * kDnChunk + pos] = (uint8_t)((meta >> 16) & 0xFFu);
+                __syncwarp();
+                if (lane == 0 && consumed(sig * sig, 0.0, 0.0)) mbar_arrive(a_ready);   // bucket loads have returned
+                const int chunks = p.n + (has_flat ? 1 : 0);
+                for (int k = 0; k < chunks; ++k) {
+                    mbar_wait(&full[s], phase);
+                    const bool hit = mine && ke == k;
+                    if (hit) reinterpret_cast<double*>(ring + (size_t)s * kStdChunk)[pos] = sig;
+                    if (__any_sync(0xffffffffu, hit))
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // before the TMA refill
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ready[s]);
+                    if (++s == stages) { s = 0; phase ^= 1; }
+                }
+            }
+        }
     } else {
         // ===== consumers: thread tid owns pixel tid of each tile =====
+        uint64_t* const c_full = patched ? ready : full;          // what "stage is ready" means
+        uint64_t* const c_afull = patched ? a_ready : a_full;
         const double* myA = lutA + (lane & (kLutACopies - 1));
         const double2* myB = lutB + (lane & (kLutBCopies - 1));
         uint32_t ti = 0, phase = 0;
@@ -178,7 +226,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
             const int64_t px = (int64_t)tile * kTilePx + tid;
             // ---- pass A: sum of weights; pack the DNs of every exposure into registers ----
-            mbar_wait(a_full, ti & 1);
+            mbar_wait(c_afull, ti & 1);
             uint32_t pk[NMAX];
             double S0 = 0.0, S1 = 0.0, S2 = 0.0;
 #pragma unroll
@@ -207,7 +255,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
 #pragma unroll
             for (int k = 0; k < NMAX; ++k) {
                 if (k < p.n) {
-                    mbar_wait(&full[s], phase);
+                    mbar_wait(&c_full[s], phase);
                     const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
                     const double g0 = sp[0], g1 = sp[1], g2 = sp[2];
                     const uint32_t q = pk[k];
@@ -230,7 +278,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             double u0 = sqrt(as0) * r0, u1 = sqrt(as1) * r1, u2 = sqrt(as2) * r2;
             const int64_t i0 = px * kC;
             if (has_flat) {
-                mbar_wait(&full[s], phase);
+                mbar_wait(&c_full[s], phase);
                 const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
                 const double f0 = sp[0], f1 = sp[1], f2 = sp[2];
                 double fv0, fv1, fv2;
@@ -261,6 +309,7 @@ bool make_layout(const MergeParams& p, StagedLayout& L) {
     L.off_lutA = off; off += 256 * kLutACopies * 8;
     L.off_lutB = off; off += kC * 256 * kLutBCopies * 16;
     L.off_abuf_dn = off; off += (uint32_t)(p.n + (p.flat_bytes == 1 ? 1 : 0)) * kDnChunk;
+    L.off_bucket = off; if (p.any_dark) off += kBucketWords * 4;
     off = (off + 127) & ~127u;
     L.off_ring = off;
     const size_t room = kSmemLimit - 256 - off;
@@ -278,7 +327,7 @@ bool make_layout(const MergeParams& p, StagedLayout& L) {
 bool merge_staged_supported(const MergeParams& p, bool all_std_images) {
     if (p.C != kC || p.bits != 256 || p.max_dn != 255.0 || !all_std_images) return false;
     if ((int64_t)p.H * p.W < kTilePx || (int64_t)p.H * p.W * kC >= 0xFFFFFFFFll) return false;
-    if (p.any_dark && (!p.hot_list || p.hot_cap == 0)) return false;
+    if (p.any_dark && (!p.hot_list || p.hot_cap == 0 || !p.buckets)) return false;
     if (p.flat_bytes && (!aligned(p.flat_std, 16) || !aligned(p.flat, 16))) return false;
     StagedLayout L;
     return make_layout(p, L);
