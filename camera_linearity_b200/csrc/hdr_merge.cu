@@ -255,29 +255,35 @@ __device__ __noinline__ void file_patch(const MergeParams& p, int k, uint32_t sa
 }
 
 constexpr int kScanLocal = 1024;
+constexpr int kHitsHeader = 2;              // uint2 entries in front of the hit list
 
-// Two phases per block iteration so that the gather-heavy median work is not serialised inside
-// diverged warps: (1) every thread compares 64 dark bytes and pushes its (rare) hits to a
-// shared-memory list, (2) the CTA drains the list with one hit per thread.
+// Pass 1: pure streaming compare; hits are staged per CTA and flushed with one global atomic.
 __global__ void __launch_bounds__(kScanThreads)
 dark_scan_kernel(const __grid_constant__ MergeParams p) {
     __shared__ uint2 s_hits[kScanLocal];        // {sample, exposure}
-    __shared__ uint32_t s_count;
+    __shared__ uint32_t s_count, s_base;
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
     const int64_t n = (int64_t)p.H * p.W * p.C;
     const int64_t n_vec = (n + 15) / 16;        // the last vector may be ragged
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t* g_count = &p.hits[0].x;
 
+    auto push_global = [&](uint32_t slot, uint2 h) {
+        if (slot < p.hot_cap) p.hits[kHitsHeader + slot] = h;
+    };
     auto hit = [&](int k, uint32_t sample) {
         const uint32_t slot = atomicAdd(&s_count, 1u);
-        if (slot < kScanLocal) s_hits[slot] = make_uint2(sample, (uint32_t)k);
-        else file_patch(p, k, sample);           // dense bad region: no room, repair right here
+        const uint2 h = make_uint2(sample, (uint32_t)k);
+        if (slot < kScanLocal) s_hits[slot] = h;
+        else push_global(atomicAdd(g_count, 1u), h);          // dense bad region
     };
-    auto drain = [&]() {                         // block-uniform call sites only
+    auto flush = [&]() {                                      // block-uniform call sites only
         __syncthreads();
         const uint32_t cnt = min(s_count, (uint32_t)kScanLocal);
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) file_patch(p, (int)s_hits[i].y, s_hits[i].x);
+        if (threadIdx.x == 0) s_base = atomicAdd(g_count, cnt);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) push_global(s_base + i, s_hits[i]);
         __syncthreads();
         if (threadIdx.x == 0) s_count = 0;
         __syncthreads();
@@ -317,10 +323,26 @@ dark_scan_kernel(const __grid_constant__ MergeParams p) {
             __syncthreads();
             const uint32_t pending = s_count;    // read between two barriers: block-uniform
             __syncthreads();
-            if (pending >= kScanThreads) drain();
+            if (pending >= kScanLocal / 2) flush();
         }
     }
-    drain();
+    flush();
+}
+
+// Pass 2: one thread per hit computes the medians and files the patch -- fully parallel, so the
+// gather latency is paid once instead of serially inside diverged warps of the streaming pass.
+__global__ void __launch_bounds__(128)
+dark_patch_kernel(const __grid_constant__ MergeParams p) {
+    const uint32_t count = p.hits[0].x;
+    if (count > p.hot_cap) {                      // hit list overflowed: force the fix-up's rescan mode
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.hot_list[0] = 0xFFFFFFFFu;
+        return;
+    }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const uint2 h = p.hits[kHitsHeader + i];
+        file_patch(p, (int)h.y, h.x);
+    }
 }
 
 // Full recomputation of one sample with the bad-pixel repair, same arithmetic (and the same
@@ -518,7 +540,12 @@ int launch_dark_scan(const MergeParams& p, cudaStream_t stream) {
     // zero the 16-byte header (count) of every tile bucket
     e = cudaMemset2DAsync(p.buckets, kBucketWords * sizeof(uint32_t), 0, 16, (size_t)p.n_full_tiles, stream);
     if (e != cudaSuccess) return cuda_status(e);
-    dark_scan_kernel<<<sm_count() * 4, kScanThreads, 0, stream>>>(p);
+    e = cudaMemsetAsync(p.hits, 0, kHitsHeader * sizeof(uint2), stream);
+    if (e != cudaSuccess) return cuda_status(e);
+    dark_scan_kernel<<<sm_count() * 8, kScanThreads, 0, stream>>>(p);
+    int st = launched();
+    if (st != CL_OK) return st;
+    dark_patch_kernel<<<sm_count() * 8, 128, 0, stream>>>(p);
     return launched();
 }
 
@@ -552,7 +579,8 @@ size_t cl_hdr_merge_workspace_bytes(const cl_hdr_merge_args* a) {
     if (any_dark && a->dn_bytes == 1 && a->channels == 3 && a->algo != 1)
         bytes += (cl::kHotListHeader + cl::hot_list_entries((int64_t)a->height * a->width * a->channels)) *
                      sizeof(uint32_t) +
-                 cl::bucket_bytes((int64_t)a->height * a->width) + 16;
+                 cl::bucket_bytes((int64_t)a->height * a->width) + 16 +
+                 (cl::kHitsHeader + cl::hot_list_entries((int64_t)a->height * a->width * a->channels)) * sizeof(uint2);
     return bytes;
 }
 
@@ -634,8 +662,11 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
         const size_t off = tab_smem ? 0 : table_bytes(p.bits, p.C);
         const size_t entries = hot_list_entries((int64_t)p.H * p.W * p.C);
         const size_t list_bytes = ((kHotListHeader + entries) * sizeof(uint32_t) + 15) / 16 * 16;
+        const size_t bkt_bytes = (bucket_bytes((int64_t)p.H * p.W) + 15) / 16 * 16;
+        const size_t hits_bytes = (kHitsHeader + entries) * sizeof(uint2);
         if (workspace && aligned(workspace, 16) &&
-            workspace_bytes >= off + list_bytes + bucket_bytes((int64_t)p.H * p.W)) {
+            workspace_bytes >= off + list_bytes + bkt_bytes + hits_bytes) {
+            p.hits = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(workspace) + off + list_bytes + bkt_bytes);
             p.hot_list = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + off);
             p.hot_cap = (uint32_t)entries;
             p.buckets = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + off + list_bytes);

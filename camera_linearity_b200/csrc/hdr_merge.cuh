@@ -37,6 +37,8 @@ struct MergeParams {
     int32_t n_full_tiles;      // 512-pixel tiles handled by the staged kernel
     // per-tile bad-pixel patch buckets (staged path): [count, pad x3][kBucketCap x {meta, pad, sigma}]
     uint32_t* buckets;
+    // bad (sample, exposure) pairs found by the dark scan: hits[0].x = count, entries from hits[2]
+    uint2* hits;
 };
 
 constexpr size_t kHotListHeader = 4;   // uint32 entries reserved in front of the list (counter + pad)
@@ -104,17 +106,18 @@ __device__ __noinline__ double median_std(const double* __restrict__ std_img,
     return select_rank(win, m, (K * K) / 2);
 }
 
-// normalize_by_map, measurand.py:586-602 (operand order kept; true divisions, once per sample).
+// normalize_by_map, measurand.py:586-602, with ONE division: rf = 1/flat, then
+//   val' = val*rf*m ;  std' = sqrt( (sd*rf*m)^2 + (val*rf^2*fs*m)^2 + (val*rf*ms)^2 )
+// (the reference's three quotients share the divisor; <= a few ulp from its operand order).
 __device__ __forceinline__ void flat_epilogue(double& val, double& sd, double fv, double fs, double m,
                                               double ms) {
-    const double fv2 = fv * fv;
-    const double m2 = m * m;
-    const double v2 = val * val;
-    const double u_acq = ((sd * sd) / fv2) * m2;
-    const double u_ff = ((v2 / (fv2 * fv2)) * (fs * fs)) * m2;
-    const double u_ffm = (v2 / fv2) * (ms * ms);
-    sd = sqrt(u_acq + u_ff + u_ffm);
-    val = (val / fv) * m;
+    const double rf = 1.0 / fv;
+    const double vr = val * rf;            // val / flat
+    const double t1 = (sd * rf) * m;
+    const double t2 = ((vr * rf) * fs) * m;
+    const double t3 = vr * ms;
+    sd = sqrt(fma(t1, t1, fma(t2, t2, t3 * t3)));
+    val = vr * m;
 }
 
 __device__ __forceinline__ double flat_value(const void* flat, int flat_bytes, int64_t i,

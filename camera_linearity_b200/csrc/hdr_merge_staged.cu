@@ -96,6 +96,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // compares false), but the compiler cannot prove it, so the mbarrier arrive is ordered after the
 // arithmetic that consumed the loads and the scoreboard guarantees they have returned.
 __device__ __forceinline__ bool consumed(double a, double b, double c) { return !((a + b) + c < 0.0); }
+// Same idea on the integer pipe for the per-exposure release (the FP64 pipe is the busier one):
+// the variance accumulators are sums of squares, so their sign bits are clear -- also for NaN,
+// because CUDA arithmetic returns the canonical (positive) quiet NaN.
+__device__ __forceinline__ bool consumed_nonneg(double a, double b, double c) {
+    return (__double2hiint(a) | __double2hiint(b) | __double2hiint(c)) >= 0;
+}
 
 template <int NMAX>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -269,7 +275,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
                     merge_accumulate(w1, e1.x, e1.y, kappa_of(d1, p.kappa_scale), g1, r1, rt, av1, as1);
                     merge_accumulate(w2, e2.x, e2.y, kappa_of(d2, p.kappa_scale), g2, r2, rt, av2, as2);
                     __syncwarp();
-                    if (lane == 0 && consumed(as0, as1, as2)) mbar_arrive(&empty[s]);
+                    if (lane == 0 && consumed_nonneg(as0, as1, as2)) mbar_arrive(&empty[s]);
                     if (++s == stages) { s = 0; phase ^= 1; }
                 }
             }
