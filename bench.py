@@ -266,6 +266,8 @@ def run_ours(args, wl):
     import camera_linearity_b200 as cl
     from camera_linearity_b200 import _lib, ops, parallel
 
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     rank, world, local = parallel.init_from_env()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     dev = torch.device("cuda", local)
@@ -334,7 +336,7 @@ def run_ours(args, wl):
     torch.cuda.empty_cache()
     feats = lambda tk, subject: {"illumination": "bf", "magnification": "10x", "exposure": tk, "subject": subject}
 
-    def e2e_step():
+    def e2e_step(out_host):
         sets = [cl.ImageSet(features=feats(t[k], "s"), measurand=cl.Measurand(None, host["std"][k].to(dev, non_blocking=True)))
                 for k in range(wl["N"])]
         for k, s in enumerate(sets):
@@ -356,19 +358,26 @@ def run_ours(args, wl):
         out_host[0].copy_(m.val, non_blocking=True)
         out_host[1].copy_(m.std, non_blocking=True)
 
-    n_e2e = max(1, min(args.steps, 3))
-    e2e_step()
+    # Two CUDA streams alternate between steps so that the device->host read of step i overlaps the
+    # host->device copies of step i+1 (PCIe is full duplex); every step still moves all of its inputs
+    # and reads back its whole result inside the timed region.
+    n_e2e = max(2, min(args.steps, 4))
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    out_hosts = [out_host, (torch.empty_like(out_host[0]).pin_memory(), torch.empty_like(out_host[1]).pin_memory())]
+
+    def e2e_run(count):
+        for i in range(count):
+            with torch.cuda.stream(streams[i % 2]):
+                e2e_step(out_hosts[i % 2])
+        for st in streams:
+            st.synchronize()
+
+    e2e_run(2)
     barrier()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
-    e0.record()
-    for _ in range(n_e2e):
-        e2e_step()
-    e1.record()
+    e2e_run(n_e2e)
     barrier()
-    wall = time.perf_counter() - wall0
-    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+    e2e_ms = (time.perf_counter() - wall0) * 1e3
     tm = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -385,6 +394,9 @@ def run_ours(args, wl):
         except Exception as exc:          # the headline must not die on an auxiliary measurement
             extra = {"error": repr(exc)}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = hbm_peak()
@@ -404,9 +416,11 @@ def run_ours(args, wl):
                      "traffic": None, "peak_source": peak_src, "kernel": "merge_staged_kernel" if args.algo != 1 else "merge_generic_kernel",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": "Gpix*exposures/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": e2e_value, "unit": "Gpix*exposures/s", "h2d_bytes_per_step": world * h2d,
+                "d2h_bytes_per_step": world * d2h,
                 "ms_per_step": float(tm.item()) / n_e2e, "steps": n_e2e,
-                "api": "ExposureSeries.process_HDR_image from pinned host tensors"},
+                "api": "ExposureSeries.process_HDR_image from pinned host tensors; steps alternate between two "
+                       "CUDA streams (D2H of step i overlaps H2D of step i+1); wall-clock timed"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "extra": extra,

@@ -40,7 +40,10 @@ def init_from_env(backend: str | None = None) -> Tuple[int, int, int]:
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend=backend, rank=rk, world_size=ws)
+        kwargs = {}
+        if backend == "nccl":
+            kwargs["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rk, world_size=ws, **kwargs)
     return rk, ws, local
 
 
