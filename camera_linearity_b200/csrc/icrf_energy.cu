@@ -17,8 +17,6 @@ namespace cl {
 namespace {
 
 constexpr int kGroup = 32;            // candidates per warp
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kMaxN = CL_MAX_PAIR_EXPOSURES;
 
 __host__ __device__ inline int n_pairs(int n) { return n * (n - 1) / 2; }
@@ -80,8 +78,65 @@ __global__ void curves_kernel(const cl_icrf_problem prob, const double* __restri
 }
 
 // ---- partial energies -----------------------------------------------------------------------------
+// One pixel per warp-iteration, two pixels in flight (the DN / sigma loads of the next pixel are
+// issued before the arithmetic of the current one).  No branches in the pair loop: invalid pairs
+// contribute exact zeros.
 template <int N, bool USE_STD>
-__global__ void __launch_bounds__(kThreads, 1)
+struct PixelData {
+    int bin[N];
+    double sg[USE_STD ? N : 1];
+};
+
+template <int N, bool USE_STD>
+__device__ __forceinline__ void load_pixel(PixelData<N, USE_STD>& d, const uint8_t* __restrict__ dn,
+                                           const double* __restrict__ sd, int64_t px, int D) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        d.bin[k] = min((int)__ldg(dn + px * N + k), D - 1);        // callers guarantee dn < D
+        if (USE_STD) d.sg[USE_STD ? k : 0] = __ldg(sd + px * N + k);
+    }
+}
+
+template <int N, bool USE_STD, int P>
+__device__ __forceinline__ void accumulate_pixel(const PixelData<N, USE_STD>& d, const double2* __restrict__ tab,
+                                                 int lane, const PairRatios& inv_ratio, double (&num)[P],
+                                                 double (&den)[P]) {
+    double I[N], R[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double2 e = tab[d.bin[k] * kGroup + lane];
+        I[k] = e.x;
+        R[k] = e.y;
+    }
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = i + 1; j < N; ++j, ++q) {
+            const double m = R[j] * inv_ratio.v[q];   // 1 / (I_j * r)
+            const double u = I[i] * m;                // I_i / scaled
+            const double a = fabs(u - 1.0);           // |I_i - scaled| / scaled, :115-121
+            if (!USE_STD) {
+                const bool ok = a == a;               // nanmean, :139 (inf is kept, as NumPy does)
+                num[q] += ok ? a : 0.0;
+                den[q] += ok ? 1.0 : 0.0;
+            } else {
+                const double t1 = d.sg[USE_STD ? i : 0] * m;                       // sigma_i / scaled
+                const double t2 = u * (d.sg[USE_STD ? j : 0] * R[j]);              // I_i sigma_j / (r I_j^2)
+                const double var = fma(t1, t1, t2 * t2);                           // :128
+                // finite |d|, sigma != 0, weight 1/sigma not NaN (:134-135, gf.nanaverage)
+                const bool ok = (a < inf) && (var > 0.0);
+                const double w = ok ? rsqrt(var) : 0.0;
+                num[q] = fma(ok ? a : 0.0, w, num[q]);
+                den[q] += w;
+            }
+        }
+    }
+}
+
+template <int N, bool USE_STD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 energy_partial_kernel(const double2* __restrict__ tables, int D, const uint8_t* __restrict__ dn,
                       const double* __restrict__ sd, int64_t n_pixels, int64_t px_per_cta,
                       const __grid_constant__ PairRatios inv_ratio /* [pairs] = t_j / t_i */,
@@ -91,7 +146,7 @@ energy_partial_kernel(const double2* __restrict__ tables, int D, const uint8_t* 
     double2* tab = reinterpret_cast<double2*>(smem_raw);           // [D][32]
     const int group = blockIdx.y;
     const double2* src = tables + (int64_t)group * D * kGroup;
-    for (int i = threadIdx.x; i < D * kGroup; i += kThreads) tab[i] = src[i];
+    for (int i = threadIdx.x; i < D * kGroup; i += WARPS * 32) tab[i] = src[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,58 +155,44 @@ energy_partial_kernel(const double2* __restrict__ tables, int D, const uint8_t* 
     for (int q = 0; q < P; ++q) { num[q] = 0.0; den[q] = 0.0; }
     const int64_t first = (int64_t)blockIdx.x * px_per_cta;
     const int64_t last = min(n_pixels, first + px_per_cta);
-    for (int64_t px = first + warp; px < last; px += kWarps) {
-        const uint8_t* dp = dn + px * N;
-        double I[N], R[N], sg[N];
+    int64_t px = first + warp;
+    PixelData<N, USE_STD> cur, nxt;
+    if (px < last) load_pixel<N, USE_STD>(cur, dn, sd, px, D);
+    for (; px < last; px += WARPS) {
+        const int64_t pn = px + WARPS;
+        if (pn < last) load_pixel<N, USE_STD>(nxt, dn, sd, pn, D);     // prefetch
+        accumulate_pixel<N, USE_STD, P>(cur, tab, lane, inv_ratio, num, den);
+        cur = nxt;
+    }
+
+    // combine the CTA's warps with a fixed-order tree through shared memory (table space reused)
+    double* red = reinterpret_cast<double*>(smem_raw);             // [half][2P][32]
+    for (int half = WARPS / 2; half >= 1; half >>= 1) {
+        __syncthreads();
+        if (warp >= half && warp < 2 * half) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-            const int bin = min((int)__ldg(dp + k), D - 1);      // callers guarantee dn < D
-            const double2 e = tab[bin * kGroup + lane];
-            I[k] = e.x;
-            R[k] = e.y;
-            if (USE_STD) sg[k] = __ldg(sd + px * N + k);
+            for (int q = 0; q < P; ++q) {
+                red[(((warp - half) * 2 * P) + 2 * q) * 32 + lane] = num[q];
+                red[(((warp - half) * 2 * P) + 2 * q + 1) * 32 + lane] = den[q];
+            }
         }
-        int q = 0;
+        __syncthreads();
+        if (warp < half) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-#pragma unroll
-            for (int j = i + 1; j < N; ++j, ++q) {
-                const double m = R[j] * inv_ratio.v[q];   // 1 / (I_j * r)
-                const double u = I[i] * m;                // I_i / scaled
-                const double a = fabs(u - 1.0);           // |I_i - scaled| / scaled, :115-121
-                if (!USE_STD) {
-                    if (a == a) { num[q] += a; den[q] += 1.0; }           // nanmean, :139
-                } else {
-                    const double t1 = sg[i] * m;                          // sigma_i / scaled
-                    const double t2 = u * (sg[j] * R[j]);                 // I_i sigma_j / (r I_j^2)
-                    const double var = fma(t1, t1, t2 * t2);              // :128
-                    // finite |d|, sigma != 0, weight 1/sigma not NaN (:134-135, gf.nanaverage)
-                    if (a < __longlong_as_double(0x7ff0000000000000LL) && var > 0.0) {
-                        const double w = rsqrt(var);
-                        num[q] = fma(a, w, num[q]);
-                        den[q] += w;
-                    }
-                }
+            for (int q = 0; q < P; ++q) {
+                num[q] += red[((warp * 2 * P) + 2 * q) * 32 + lane];
+                den[q] += red[((warp * 2 * P) + 2 * q + 1) * 32 + lane];
             }
         }
     }
-
-    // combine the CTA's warps in a fixed order (reuse the table space)
-    __syncthreads();
-    double* red = reinterpret_cast<double*>(smem_raw);             // [warp][2P][32]
+    if (warp == 0) {
+        const int s = group * kGroup + lane;
+        double* out = cta_partial + (((int64_t)blockIdx.x * S + s) * P) * 2;
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-        red[((warp * 2 * P) + 2 * q) * 32 + lane] = num[q];
-        red[((warp * 2 * P) + 2 * q + 1) * 32 + lane] = den[q];
-    }
-    __syncthreads();
-    const int cta = blockIdx.x;
-    for (int idx = threadIdx.x; idx < 2 * P * 32; idx += kThreads) {
-        const int l = idx & 31, qq = idx >> 5;
-        double sum = 0.0;
-        for (int w = 0; w < kWarps; ++w) sum += red[((w * 2 * P) + qq) * 32 + l];
-        const int s = group * kGroup + l;
-        cta_partial[(((int64_t)cta * S + s) * P) * 2 + qq] = sum;
+        for (int q = 0; q < P; ++q) {
+            out[2 * q] = num[q];
+            out[2 * q + 1] = den[q];
+        }
     }
 }
 
@@ -197,7 +238,7 @@ inline Plan make_plan(const cl_icrf_problem& p, int64_t n_pixels) {
     pl.groups = p.n_candidates / kGroup;
     int chunks = sm_count() / (pl.groups > 0 ? pl.groups : 1);
     if (chunks < 1) chunks = 1;
-    const int64_t min_px = kWarps * 8;     // do not split tiny problems into idle CTAs
+    const int64_t min_px = 16 * 8;         // do not split tiny problems into idle CTAs
     if ((int64_t)chunks * min_px > n_pixels) chunks = (int)((n_pixels + min_px - 1) / min_px);
     if (chunks < 1) chunks = 1;
     pl.chunks = chunks;
@@ -216,18 +257,19 @@ template <int N>
 int launch_partial(const cl_icrf_problem& p, const Plan& pl, const double2* tables, const uint8_t* dn,
                    const double* sd, int64_t n_pixels, const PairRatios& inv_ratio, double* cta_partial,
                    cudaStream_t stream) {
+    constexpr int WARPS = N <= 6 ? 16 : 8;         // registers: 2P accumulators per lane
     const size_t tab_bytes = (size_t)p.datapoints * kGroup * sizeof(double2);
-    const size_t red_bytes = (size_t)kWarps * 2 * n_pairs(N) * 32 * sizeof(double);
+    const size_t red_bytes = (size_t)(WARPS / 2) * 2 * n_pairs(N) * 32 * sizeof(double);
     const size_t smem = tab_bytes > red_bytes ? tab_bytes : red_bytes;
     dim3 grid(pl.chunks, pl.groups);
     auto go = [&](auto kernel) -> int {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_status(e);
-        kernel<<<grid, kThreads, smem, stream>>>(tables, p.datapoints, dn, sd, n_pixels, pl.px_per_cta,
-                                                 inv_ratio, cta_partial, p.n_candidates);
+        kernel<<<grid, WARPS * 32, smem, stream>>>(tables, p.datapoints, dn, sd, n_pixels, pl.px_per_cta,
+                                                   inv_ratio, cta_partial, p.n_candidates);
         return launched();
     };
-    return sd ? go(energy_partial_kernel<N, true>) : go(energy_partial_kernel<N, false>);
+    return sd ? go(energy_partial_kernel<N, true, WARPS>) : go(energy_partial_kernel<N, false, WARPS>);
 }
 
 }  // namespace
