@@ -167,19 +167,19 @@ merge_generic_kernel(const __grid_constant__ MergeParams p, const int64_t first_
 
         double ov[kVec], os[kVec];
 #pragma unroll
-        for (int j = 0; j < kVec; ++j) {
-            ov[j] = av[j] * rS[j];
-            os[j] = sqrt(as[j]) * rS[j];
-        }
+        for (int j = 0; j < kVec; ++j) ov[j] = av[j] * rS[j];
         if (p.flat_bytes) {
 #pragma unroll
             for (int j = 0; j < kVec; ++j) {
-                if (base + j < n) {
-                    const double fv = flat_value(p.flat, p.flat_bytes, base + j, p.max_dn);
-                    flat_epilogue(ov[j], os[j], fv, p.flat_std[base + j], p.flat_means[cidx[j]],
-                                  p.flat_means[C + cidx[j]]);
-                }
+                os[j] = 0.0;
+                if (base + j < n)
+                    flat_apply(ov[j], os[j], (as[j] * rS[j]) * rS[j],
+                               flat_recip(p.flat, p.flat_bytes, base + j, p.max_dn), p.flat_std[base + j],
+                               p.flat_means[cidx[j]], p.flat_means[C + cidx[j]]);
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kVec; ++j) os[j] = sqrt(as[j]) * rS[j];
         }
         if (base + kVec <= n) {
             *reinterpret_cast<double2*>(p.out_val + base) = make_double2(ov[0], ov[1]);
@@ -320,10 +320,7 @@ dark_scan_kernel(const __grid_constant__ MergeParams p) {
                         if (bytes[i] >= p.hot_dn[k]) hit(k, (uint32_t)i);
                 }
             }
-            __syncthreads();
-            const uint32_t pending = s_count;    // read between two barriers: block-uniform
-            __syncthreads();
-            if (pending >= kScanLocal / 2) flush();
+            // no barrier in the streaming loop: a full local list spills to the global one (hit())
         }
     }
     flush();
@@ -384,10 +381,12 @@ __device__ __noinline__ void recompute_sample(const MergeParams& p, int64_t i) {
         merge_accumulate(w, p1, p.dlut[(int64_t)d * C + c], kappa_of(d, p.kappa_scale), sg, rS, p.inv_t[k],
                          av, as);
     }
-    double ov = av * rS, os = sqrt(as) * rS;
+    double ov = av * rS, os;
     if (p.flat_bytes)
-        flat_epilogue(ov, os, flat_value(p.flat, p.flat_bytes, i, p.max_dn), p.flat_std[i], p.flat_means[c],
-                      p.flat_means[C + c]);
+        flat_apply(ov, os, (as * rS) * rS, flat_recip(p.flat, p.flat_bytes, i, p.max_dn), p.flat_std[i],
+                   p.flat_means[c], p.flat_means[C + c]);
+    else
+        os = sqrt(as) * rS;
     p.out_val[i] = ov;
     p.out_std[i] = os;
 }
@@ -513,7 +512,7 @@ __global__ void flat_normalize_kernel(const double* __restrict__ val, const doub
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int c = (int)(i % C);
         double v = val[i], s = std[i];
-        flat_epilogue(v, s, fv[i], fs[i], means[c], means[C + c]);
+        flat_apply(v, s, s * s, 1.0 / fv[i], fs[i], means[c], means[C + c]);
         out_val[i] = v;
         out_std[i] = s;
     }

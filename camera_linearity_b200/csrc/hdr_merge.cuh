@@ -106,25 +106,44 @@ __device__ __noinline__ double median_std(const double* __restrict__ std_img,
     return select_rank(win, m, (K * K) / 2);
 }
 
-// normalize_by_map, measurand.py:586-602, with ONE division: rf = 1/flat, then
-//   val' = val*rf*m ;  std' = sqrt( (sd*rf*m)^2 + (val*rf^2*fs*m)^2 + (val*rf*ms)^2 )
-// (the reference's three quotients share the divisor; <= a few ulp from its operand order).
-__device__ __forceinline__ void flat_epilogue(double& val, double& sd, double fv, double fs, double m,
-                                              double ms) {
-    const double rf = 1.0 / fv;
+// normalize_by_map, measurand.py:586-602, in variance form with rf = 1/flat:
+//   val' = val*rf*m ;  std' = sqrt( var*(rf*m)^2 + (val*rf^2*fs*m)^2 + (val*rf*ms)^2 ),  var = std^2
+// The reference's three quotients share the divisor, so one reciprocal serves all of them, and the
+// merge kernels pass var = acc*rS^2 directly: one square root per sample instead of two.
+__device__ __forceinline__ void flat_apply(double& val, double& sd_out, double var, double rf, double fs,
+                                           double m, double ms) {
     const double vr = val * rf;            // val / flat
-    const double t1 = (sd * rf) * m;
+    const double k1 = rf * m;
     const double t2 = ((vr * rf) * fs) * m;
     const double t3 = vr * ms;
-    sd = sqrt(fma(t1, t1, fma(t2, t2, t3 * t3)));
+    sd_out = sqrt(fma(var, k1 * k1, fma(t2, t2, t3 * t3)));
     val = vr * m;
 }
+
+// 1 / (dn / 255) for 8-bit flats, correctly rounded at compile time (identical to the two device
+// divisions it replaces); dn = 0 -> +inf like IEEE division.
+struct RecipTable {
+    double v[256];
+};
+constexpr RecipTable make_recip255() {
+    RecipTable t{};
+    t.v[0] = __builtin_huge_val();
+    for (int d = 1; d < 256; ++d) t.v[d] = 1.0 / (static_cast<double>(d) / 255.0);
+    return t;
+}
+static __device__ const RecipTable kRecip255 = make_recip255();
 
 __device__ __forceinline__ double flat_value(const void* flat, int flat_bytes, int64_t i,
                                              double max_dn) {
     if (flat_bytes == 8) return reinterpret_cast<const double*>(flat)[i];
     if (flat_bytes == 2) return __ddiv_rn((double)reinterpret_cast<const uint16_t*>(flat)[i], max_dn);
     return __ddiv_rn((double)reinterpret_cast<const uint8_t*>(flat)[i], max_dn);
+}
+
+// reciprocal of the flat value of sample i
+__device__ __forceinline__ double flat_recip(const void* flat, int flat_bytes, int64_t i, double max_dn) {
+    if (flat_bytes == 1) return kRecip255.v[reinterpret_cast<const uint8_t*>(flat)[i]];
+    return 1.0 / flat_value(flat, flat_bytes, i, max_dn);
 }
 
 int launch_merge_staged(const MergeParams& p, cudaStream_t stream);   // hdr_merge_staged.cu

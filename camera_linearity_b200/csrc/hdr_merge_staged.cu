@@ -281,28 +281,30 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             }
 
             double v0 = av0 * r0, v1 = av1 * r1, v2 = av2 * r2;
-            double u0 = sqrt(as0) * r0, u1 = sqrt(as1) * r1, u2 = sqrt(as2) * r2;
+            double u0, u1, u2;
             const int64_t i0 = px * kC;
             if (has_flat) {
                 mbar_wait(&c_full[s], phase);
                 const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
                 const double f0 = sp[0], f1 = sp[1], f2 = sp[2];
-                double fv0, fv1, fv2;
+                double rf0, rf1, rf2;
                 if (flat_u8) {
-                    fv0 = __ddiv_rn((double)(pkf & 0xFF), p.max_dn);
-                    fv1 = __ddiv_rn((double)((pkf >> 8) & 0xFF), p.max_dn);
-                    fv2 = __ddiv_rn((double)(pkf >> 16), p.max_dn);
+                    rf0 = kRecip255.v[pkf & 0xFF];
+                    rf1 = kRecip255.v[(pkf >> 8) & 0xFF];
+                    rf2 = kRecip255.v[pkf >> 16];
                 } else {
-                    fv0 = flat_value(p.flat, p.flat_bytes, i0 + 0, p.max_dn);
-                    fv1 = flat_value(p.flat, p.flat_bytes, i0 + 1, p.max_dn);
-                    fv2 = flat_value(p.flat, p.flat_bytes, i0 + 2, p.max_dn);
+                    rf0 = flat_recip(p.flat, p.flat_bytes, i0 + 0, p.max_dn);
+                    rf1 = flat_recip(p.flat, p.flat_bytes, i0 + 1, p.max_dn);
+                    rf2 = flat_recip(p.flat, p.flat_bytes, i0 + 2, p.max_dn);
                 }
-                flat_epilogue(v0, u0, fv0, f0, p.flat_means[0], p.flat_means[kC + 0]);
-                flat_epilogue(v1, u1, fv1, f1, p.flat_means[1], p.flat_means[kC + 1]);
-                flat_epilogue(v2, u2, fv2, f2, p.flat_means[2], p.flat_means[kC + 2]);
+                flat_apply(v0, u0, (as0 * r0) * r0, rf0, f0, p.flat_means[0], p.flat_means[kC + 0]);
+                flat_apply(v1, u1, (as1 * r1) * r1, rf1, f1, p.flat_means[1], p.flat_means[kC + 1]);
+                flat_apply(v2, u2, (as2 * r2) * r2, rf2, f2, p.flat_means[2], p.flat_means[kC + 2]);
                 __syncwarp();
                 if (lane == 0 && consumed(u0, u1, u2)) mbar_arrive(&empty[s]);
                 if (++s == stages) { s = 0; phase ^= 1; }
+            } else {
+                u0 = sqrt(as0) * r0; u1 = sqrt(as1) * r1; u2 = sqrt(as2) * r2;
             }
             p.out_val[i0 + 0] = v0; p.out_val[i0 + 1] = v1; p.out_val[i0 + 2] = v2;
             p.out_std[i0 + 0] = u0; p.out_std[i0 + 1] = u1; p.out_std[i0 + 2] = u2;
