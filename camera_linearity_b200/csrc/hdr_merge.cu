@@ -222,73 +222,36 @@ int launch_generic(const MergeParams& p, bool tab_smem, int64_t first_item, cuda
     return launched();
 }
 
-// ---- bad-pixel patches (staged path) ----------------------------------------------------------------
-// Streams the dark frames once (64 bytes per thread in flight, SIMD byte compare).  For every
-// (sample, exposure) whose dark DN reaches the exposure's integer threshold it computes the K x K
-// medians of the DN and of the uncertainty (the rare, gather-heavy part) and files a patch
-// {pixel-in-tile, channel, exposure, repaired DN, repaired sigma} in the bucket of the 512-pixel
-// tile the sample belongs to.  The streaming merge kernel applies the patches of its current
-// tile from shared memory, so the repair costs it no global gathers.  Samples that do not fit a
-// bucket (more than kBucketCap bad (sample, exposure) pairs in one tile) go to the global
-// fix-up list instead and are recomputed in full by merge_fixup_kernel.
+// ---- bad-pixel buckets (staged path) ----------------------------------------------------------------
+// Streams the dark frames once (64 bytes per thread in flight, SIMD byte compare) and files every
+// (sample, exposure) whose dark DN reaches the exposure's integer threshold in the bucket of the
+// 512-pixel tile it belongs to: {pixel-in-tile, channel, exposure}.  The merge kernel's median warp
+// computes the repaired DN / sigma for its next tile's bucket while the consumers are still busy
+// with the current tile, so the repair costs neither a separate gather pass nor a stall.  Samples
+// that do not fit a bucket (more than kBucketCap bad pairs in one tile) go to the global fix-up
+// list and are recomputed in full by merge_fixup_kernel.
 constexpr int kScanThreads = 256;
 constexpr int kScanVecs = 4;
 
-__device__ __noinline__ void file_patch(const MergeParams& p, int k, uint32_t sample) {
+__device__ __forceinline__ void file_hit(const MergeParams& p, int k, uint32_t sample) {
     const uint32_t px = sample / 3u, c = sample - px * 3u;
     const uint32_t tile = px / kStagedTilePx;
     if ((int)tile >= p.n_full_tiles) return;            // ragged tail: the generic kernel repairs inline
-    const int y = (int)(px / (uint32_t)p.W), x = (int)(px - (uint32_t)y * (uint32_t)p.W);
-    const uint8_t* img = reinterpret_cast<const uint8_t*>(p.dn[k]);
-    const uint32_t d_new = median_dn(img, y, x, (int)c, p.H, p.W, 3, p.K);
-    const double s_new = median_std(p.std[k], img, p.std_lut, y, x, (int)c, p.H, p.W, 3, p.K);
     uint32_t* bucket = p.buckets + (size_t)tile * kBucketWords;
     const uint32_t slot = atomicAdd(bucket, 1u);
     if (slot < (uint32_t)kBucketCap) {
-        uint32_t* e = bucket + 4 + 4 * slot;
-        e[0] = (px - tile * kStagedTilePx) | (c << 9) | ((uint32_t)k << 11) | (d_new << 16);
-        *reinterpret_cast<double*>(e + 2) = s_new;
+        bucket[4 + 4 * slot] = (px - tile * kStagedTilePx) | (c << 9) | ((uint32_t)k << 11);
     } else {
         const uint32_t g = atomicAdd(&p.hot_list[0], 1u);
         if (g < p.hot_cap) p.hot_list[kHotListHeader + g] = sample;
     }
 }
 
-constexpr int kScanLocal = 1024;
-constexpr int kHitsHeader = 2;              // uint2 entries in front of the hit list
-
-// Pass 1: pure streaming compare; hits are staged per CTA and flushed with one global atomic.
 __global__ void __launch_bounds__(kScanThreads)
 dark_scan_kernel(const __grid_constant__ MergeParams p) {
-    __shared__ uint2 s_hits[kScanLocal];        // {sample, exposure}
-    __shared__ uint32_t s_count, s_base;
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
     const int64_t n = (int64_t)p.H * p.W * p.C;
     const int64_t n_vec = (n + 15) / 16;        // the last vector may be ragged
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    uint32_t* g_count = &p.hits[0].x;
-
-    auto push_global = [&](uint32_t slot, uint2 h) {
-        if (slot < p.hot_cap) p.hits[kHitsHeader + slot] = h;
-    };
-    auto hit = [&](int k, uint32_t sample) {
-        const uint32_t slot = atomicAdd(&s_count, 1u);
-        const uint2 h = make_uint2(sample, (uint32_t)k);
-        if (slot < kScanLocal) s_hits[slot] = h;
-        else push_global(atomicAdd(g_count, 1u), h);          // dense bad region
-    };
-    auto flush = [&]() {                                      // block-uniform call sites only
-        __syncthreads();
-        const uint32_t cnt = min(s_count, (uint32_t)kScanLocal);
-        if (threadIdx.x == 0) s_base = atomicAdd(g_count, cnt);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) push_global(s_base + i, s_hits[i]);
-        __syncthreads();
-        if (threadIdx.x == 0) s_count = 0;
-        __syncthreads();
-    };
-
     for (int k = 0; k < p.n; ++k) {
         if (!p.dark[k] || p.hot_dn[k] > 255u) continue;
         const uint32_t thr = p.hot_dn[k] * 0x01010101u;
@@ -311,34 +274,16 @@ dark_scan_kernel(const __grid_constant__ MergeParams p) {
                         uint32_t m = __vcmpgeu4(w[j], thr);
                         while (m) {
                             const int b = (__ffs(m) - 1) >> 3;
-                            hit(k, (uint32_t)(v * 16 + j * 4 + b));
+                            file_hit(p, k, (uint32_t)(v * 16 + j * 4 + b));
                             m &= ~(0xFFu << (8 * b));
                         }
                     }
                 } else if (v < n_vec) {           // ragged last vector
                     for (int64_t i = v * 16; i < n; ++i)
-                        if (bytes[i] >= p.hot_dn[k]) hit(k, (uint32_t)i);
+                        if (bytes[i] >= p.hot_dn[k]) file_hit(p, k, (uint32_t)i);
                 }
             }
-            // no barrier in the streaming loop: a full local list spills to the global one (hit())
         }
-    }
-    flush();
-}
-
-// Pass 2: one thread per hit computes the medians and files the patch -- fully parallel, so the
-// gather latency is paid once instead of serially inside diverged warps of the streaming pass.
-__global__ void __launch_bounds__(128)
-dark_patch_kernel(const __grid_constant__ MergeParams p) {
-    const uint32_t count = p.hits[0].x;
-    if (count > p.hot_cap) {                      // hit list overflowed: force the fix-up's rescan mode
-        if (blockIdx.x == 0 && threadIdx.x == 0) p.hot_list[0] = 0xFFFFFFFFu;
-        return;
-    }
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        const uint2 h = p.hits[kHitsHeader + i];
-        file_patch(p, (int)h.y, h.x);
     }
 }
 
@@ -539,12 +484,7 @@ int launch_dark_scan(const MergeParams& p, cudaStream_t stream) {
     // zero the 16-byte header (count) of every tile bucket
     e = cudaMemset2DAsync(p.buckets, kBucketWords * sizeof(uint32_t), 0, 16, (size_t)p.n_full_tiles, stream);
     if (e != cudaSuccess) return cuda_status(e);
-    e = cudaMemsetAsync(p.hits, 0, kHitsHeader * sizeof(uint2), stream);
-    if (e != cudaSuccess) return cuda_status(e);
     dark_scan_kernel<<<sm_count() * 8, kScanThreads, 0, stream>>>(p);
-    int st = launched();
-    if (st != CL_OK) return st;
-    dark_patch_kernel<<<sm_count() * 8, 128, 0, stream>>>(p);
     return launched();
 }
 
@@ -578,8 +518,7 @@ size_t cl_hdr_merge_workspace_bytes(const cl_hdr_merge_args* a) {
     if (any_dark && a->dn_bytes == 1 && a->channels == 3 && a->algo != 1)
         bytes += (cl::kHotListHeader + cl::hot_list_entries((int64_t)a->height * a->width * a->channels)) *
                      sizeof(uint32_t) +
-                 cl::bucket_bytes((int64_t)a->height * a->width) + 16 +
-                 (cl::kHitsHeader + cl::hot_list_entries((int64_t)a->height * a->width * a->channels)) * sizeof(uint2);
+                 cl::bucket_bytes((int64_t)a->height * a->width) + 16;
     return bytes;
 }
 
@@ -662,10 +601,7 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
         const size_t entries = hot_list_entries((int64_t)p.H * p.W * p.C);
         const size_t list_bytes = ((kHotListHeader + entries) * sizeof(uint32_t) + 15) / 16 * 16;
         const size_t bkt_bytes = (bucket_bytes((int64_t)p.H * p.W) + 15) / 16 * 16;
-        const size_t hits_bytes = (kHitsHeader + entries) * sizeof(uint2);
-        if (workspace && aligned(workspace, 16) &&
-            workspace_bytes >= off + list_bytes + bkt_bytes + hits_bytes) {
-            p.hits = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(workspace) + off + list_bytes + bkt_bytes);
+        if (workspace && aligned(workspace, 16) && workspace_bytes >= off + list_bytes + bkt_bytes) {
             p.hot_list = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + off);
             p.hot_cap = (uint32_t)entries;
             p.buckets = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + off + list_bytes);

@@ -37,15 +37,13 @@ struct MergeParams {
     int32_t n_full_tiles;      // 512-pixel tiles handled by the staged kernel
     // per-tile bad-pixel patch buckets (staged path): [count, pad x3][kBucketCap x {meta, pad, sigma}]
     uint32_t* buckets;
-    // bad (sample, exposure) pairs found by the dark scan: hits[0].x = count, entries from hits[2]
-    uint2* hits;
 };
 
 constexpr size_t kHotListHeader = 4;   // uint32 entries reserved in front of the list (counter + pad)
 constexpr int kStagedTilePx = 512;     // pixels per tile of the staged kernel
 constexpr int kBucketCap = 32;         // patch entries per tile; more -> the sample goes to the fix-up list
 constexpr int kBucketWords = 4 + 4 * kBucketCap;   // uint32 words per bucket (528 bytes)
-// entry meta word: pixel-in-tile [0,9) | channel [9,11) | exposure [11,16) | repaired DN [16,24)
+// entry meta word: pixel-in-tile [0,9) | channel [9,11) | exposure [11,16)
 
 // One exposure's contribution for one sample.  With S = sum of weights and rS = 1/S:
 //   val = rS * sum_k (w g) / t_k                                   exposure_series.py:388
@@ -104,6 +102,60 @@ __device__ __noinline__ double median_std(const double* __restrict__ std_img,
         }
     }
     return select_rank(win, m, (K * K) / 2);
+}
+
+// 3 x 3 fast path (the reference's default kernel size): all 18 neighbourhood loads are issued
+// together and the two medians come out of a 19-exchange selection network in registers --
+// one memory round trip instead of two plus local-memory sorting.
+template <typename T>
+__device__ __forceinline__ void cswap(T& a, T& b) {
+    const T lo = a < b ? a : b;
+    const T hi = a < b ? b : a;
+    a = lo;
+    b = hi;
+}
+template <typename T>
+__device__ __forceinline__ T median9(T (&v)[9]) {
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
+    cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]);
+    cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
+    cswap(v[4], v[2]);
+    return v[4];
+}
+
+template <typename DN>
+__device__ __forceinline__ void median_pair(const DN* __restrict__ img, const double* __restrict__ std_img,
+                                            const double* __restrict__ std_lut, int y, int x, int c, int H,
+                                            int W, int C, int K, uint32_t& d_med, double& s_med) {
+    if (K == 3) {
+        uint32_t d[9];
+        double s[9];
+        int64_t idx[9];
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = reflect_index(y + dy, H);
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx)
+                idx[(dy + 1) * 3 + dx + 1] = ((int64_t)yy * W + reflect_index(x + dx, W)) * C + c;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) d[i] = (uint32_t)img[idx[i]];
+        if (std_img) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) s[i] = std_img[idx[i]];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) s[i] = std_lut[(int64_t)d[i] * C + c];
+        }
+        d_med = median9(d);
+        s_med = median9(s);
+    } else {
+        d_med = median_dn(img, y, x, c, H, W, C, K);
+        s_med = median_std(std_img, img, std_lut, y, x, c, H, W, C, K);
+    }
 }
 
 // normalize_by_map, measurand.py:586-602, in variance form with rf = 1/flat:

@@ -1,23 +1,24 @@
 // K2 fast path ("algo 2"): bulk-copy staged HDR merge for 8-bit, 3-channel stacks on sm_100a.
 //
-// One persistent CTA per SM (grid = #SMs), 16 consumer warps + 2 producer warps + 1 patcher warp:
+// One persistent CTA per SM (grid = #SMs), 16 consumer warps + 2 producer warps + median warp + patcher warp:
 //   * producer warp 0 streams the float64 uncertainty images through a ring of shared-memory
 //     stages with cp.async.bulk (the TMA engine's 1-D bulk copy, SASS UBLKCP) and mbarrier
 //     transaction counts -- one 12 KB chunk per (tile, exposure);
-//   * producer warp 1 bulk-copies the DN bytes of ALL exposures of the next tile into the
-//     "A buffer" while the consumers are still in pass B of the current tile;
+//   * producer warp 1 bulk-copies the DN bytes of ALL exposures of the next tile (+ flat DN bytes and
+//     the tile's bad-pixel bucket) into the "A buffer" while the consumers are still in pass B of
+//     the current tile;
 //   * consumer thread t owns pixel t of the 512-pixel tile (3 interleaved samples).  Pass A sums
 //     the Gaussian weights from the A buffer and packs the DNs into one register per exposure;
 //     pass B consumes one ring stage per exposure.
-// Bad pixels (dark frame above threshold, ~0.1 % of the samples) cost this kernel no global gathers:
+// Bad pixels (dark frame above threshold, ~0.1 % of the samples) never touch the consumers' loops:
 // a median gather inside the streaming loop stalls the whole CTA through the ring (measured: 37 us
-// per tile instead of 5).  Instead `dark_scan_kernel` streams the dark frames once, computes the
-// repaired DN / sigma of every bad (sample, exposure) and files them in per-tile patch buckets;
-// the A-buffer producer brings the tile's bucket (528 B) into shared memory and a dedicated
-// PATCHER warp writes the repaired values over the staged bytes (DNs in the A buffer, sigmas in the
-// ring stage) before the consumers are told the data is ready -- the consumers' loops carry no
-// patch code at all.  Tiles with more than 32 patches spill to a global list that
-// `merge_fixup_kernel` recomputes in full afterwards.
+// per tile instead of 5).  `dark_scan_kernel` streams the dark frames once and files every bad
+// (sample, exposure) in a per-tile bucket.  Inside this kernel the MEDIAN warp takes the bucket of
+// the NEXT tile as soon as its A buffer has landed, gathers the K x K neighbourhoods from global
+// memory (one lane per bad pixel), writes the repaired DN over the staged byte and the repaired
+// sigma into the bucket; the PATCHER warp writes that sigma over ring stage (tile, k) right after
+// it lands.  Only then are a_ready / ready[s] signalled to the consumers.  Tiles with more than 32
+// bad pairs spill to a global list that `merge_fixup_kernel` recomputes in full afterwards.
 // Shared-memory tables are replicated per lane so that the random, DN-indexed gathers are bank-
 // conflict free: w[dn] as 16 copies of a double (LDS.64: half-warp lanes hit 16 distinct bank
 // pairs), {w*g, dICRF}[c][dn] as 8 copies of a double2 (LDS.128: quarter-warp lanes hit 8
@@ -33,7 +34,7 @@ namespace {
 constexpr int kTilePx = kStagedTilePx;
 constexpr int kC = 3;
 constexpr int kConsumerWarps = kTilePx / 32;
-constexpr int kThreads = kTilePx + 96;          // + ring producer, A-buffer producer and patcher warps
+constexpr int kThreads = kTilePx + 128;         // + ring producer, A-buffer producer, median and patcher warps
 constexpr int kDnChunk = kTilePx * kC;          // bytes of one exposure's DN tile
 constexpr int kStdChunk = kTilePx * kC * 8;     // bytes of one exposure's std tile
 constexpr int kLutACopies = 16;
@@ -110,7 +111,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
     double* lutA = reinterpret_cast<double*>(smem + L.off_lutA);
     double2* lutB = reinterpret_cast<double2*>(smem + L.off_lutB);
     uint8_t* abuf_dn = smem + L.off_abuf_dn;
-    const uint32_t* bucket_s = reinterpret_cast<const uint32_t*>(smem + L.off_bucket);   // [kBucketWords]
+    uint32_t* bucket_s = reinterpret_cast<uint32_t*>(smem + L.off_bucket);               // [kBucketWords]
     const bool patched = p.any_dark != 0;
     unsigned char* ring = smem + L.off_ring;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
@@ -134,7 +135,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             mbar_init(&ready[s], 1);
         }
         mbar_init(a_full, 1);
-        mbar_init(a_empty, kConsumerWarps);
+        mbar_init(a_empty, kConsumerWarps + (patched ? 1 : 0));   // + the patcher warp (it reads the bucket)
         mbar_init(a_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -190,24 +191,51 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             }
         }
     } else if (warp == kConsumerWarps + 2) {
-        // ===== patcher: applies the tile's bad-pixel patches to the staged data in shared memory =====
-        // lane e owns bucket entry e.  DN patches go into the A buffer before pass A, sigma patches
-        // into ring stage (tile, k) right after it lands; consumers wait on a_ready / ready[] instead
-        // of a_full / full[], so their loops carry no patch code and stay exact.
+        // ===== median warp: repairs the bad pixels of the NEXT tile while the consumers work =====
+        // lane e owns bucket entry e {pixel, channel, exposure} (filed by dark_scan_kernel).  It gathers
+        // the K x K neighbourhoods from global memory, writes the median DN over the staged byte in the
+        // A buffer and the median sigma into the bucket entry, then declares the A buffer ready.
+        if (patched) {
+            uint32_t ti = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+                mbar_wait(a_full, ti & 1);
+                const uint32_t n_patch = min(bucket_s[0], (uint32_t)kBucketCap);
+                if ((uint32_t)lane < n_patch) {
+                    const uint32_t meta = bucket_s[4 + 4 * lane];
+                    const int pix = (int)(meta & 511u), c = (int)((meta >> 9) & 3u), ke = (int)((meta >> 11) & 31u);
+                    const int64_t px = (int64_t)tile * kTilePx + pix;
+                    const int y = (int)(px / p.W), x = (int)(px - (int64_t)y * p.W);
+                    const uint8_t* img = reinterpret_cast<const uint8_t*>(p.dn[ke]);
+                    uint32_t d_new;
+                    double s_new;
+                    median_pair(img, p.std[ke], p.std_lut, y, x, c, p.H, p.W, kC, p.K, d_new, s_new);
+                    abuf_dn[ke * kDnChunk + pix * kC + c] = (uint8_t)d_new;
+                    *reinterpret_cast<double*>(bucket_s + 4 + 4 * lane + 2) = s_new;
+                }
+                // generic-proxy writes into buffers the TMA engine refills later
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);
+            }
+        }
+    } else if (warp == kConsumerWarps + 3) {
+        // ===== patcher: writes the repaired sigmas over ring stage (tile, k) right after it lands =====
+        // consumers wait on a_ready / ready[] instead of a_full / full[], so their loops carry no
+        // patch code and stay exact.
         if (patched) {
             uint32_t ti = 0, phase = 0;
             int s = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-                mbar_wait(a_full, ti & 1);
+                mbar_wait(a_ready, ti & 1);
                 const uint32_t n_patch = min(bucket_s[0], (uint32_t)kBucketCap);
                 const bool mine = (uint32_t)lane < n_patch;
                 const uint32_t meta = mine ? bucket_s[4 + 4 * lane] : 0u;
                 const double sig = mine ? *reinterpret_cast<const double*>(bucket_s + 4 + 4 * lane + 2) : 0.0;
                 const uint32_t pos = (meta & 511u) * kC + ((meta >> 9) & 3u);     // sample within the tile
                 const int ke = (int)((meta >> 11) & 31u);
-                if (mine) abuf_dn[ke * kDnChunk + pos] = (uint8_t)((meta >> 16) & 0xFFu);
                 __syncwarp();
-                if (lane == 0 && consumed(sig * sig, 0.0, 0.0)) mbar_arrive(a_ready);   // bucket loads have returned
+                // the bucket is in registers now: let the A-buffer producer refill (with the consumers)
+                if (lane == 0 && consumed(sig * sig, (double)meta, 0.0)) mbar_arrive(a_empty);
                 const int chunks = p.n + (has_flat ? 1 : 0);
                 for (int k = 0; k < chunks; ++k) {
                     mbar_wait(&full[s], phase);
