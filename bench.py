@@ -485,6 +485,14 @@ def extra_kernels(dev):
     ms = timed(lambda: ops.linearize(dn, sd, icrf, diff))
     out["k1_linearize"] = {"ms": ms, "GB/s": dn.numel() * 25 / ms / 1e6, "shape": "2160x3840x3 u8 + f64 std"}
     del dn, sd
+    # linearity analysis of one exposure pair (next row 8f-1): 2160x3840x3 float64 val+std, two passes of 32 B/sample
+    xv = torch.rand((2160, 3840, 3), generator=g, device=dev, dtype=torch.float64) + 0.05
+    yv = torch.rand((2160, 3840, 3), generator=g, device=dev, dtype=torch.float64) + 0.05
+    xs = torch.rand((2160, 3840, 3), generator=g, device=dev, dtype=torch.float64) * 0.02 + 0.001
+    ys = torch.rand((2160, 3840, 3), generator=g, device=dev, dtype=torch.float64) * 0.02 + 0.001
+    ms = timed(lambda: ops.pair_statistics(xv, xs, yv, ys, 0.5, [0.1] * 3, [0.9] * 3))
+    out["pair_statistics"] = {"ms": ms, "GB/s": xv.numel() * 64 / ms / 1e6, "shape": "one exposure pair 2160x3840x3 f64 val+std"}
+    del xv, yv, xs, ys
     # K3: cfg4, 600 frames 1080x1920x3
     base = torch.randint(20, 231, (1, 1080, 1920, 3), generator=g, device=dev, dtype=torch.int16)
     frames = torch.empty((600, 1080, 1920, 3), dtype=torch.uint8, device=dev)

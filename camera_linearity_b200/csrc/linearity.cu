@@ -1,0 +1,217 @@
+// Linearity analysis of one exposure pair: thresholds -> scaled difference
+// -> per-channel statistics over the two spatial axes, fused.
+// Replaces apply_thresholds (measurand.py:375-428), compute_difference (:620-655) and
+// compute_dimension_statistics(axis=(0,1)) (:318-350) as ExposureSeries.process_linearity chains
+// them (exposure_series.py:421-446): the reference materialises the absolute and relative
+// difference images with their uncertainties (4 full float64 images per pair) and then reduces
+// them; here two streaming passes over the four inputs (32 B/sample each) produce the 6 x C numbers.
+//
+// Pass 1 accumulates, per channel and for the absolute and the relative difference,
+//   weighted:   sum(w), sum(v*w) with w = 1/sigma   (np.nansum semantics: NaN terms are skipped
+//               individually), sum(sigma), count(sigma) for the mean uncertainty;
+//   unweighted: count, sum(v).
+// Pass 2 accumulates sum(w*(v-mean)^2) (or sum((v-mean)^2)).  Block partials are combined in a fixed
+// order (deterministic); the reference's pairwise summation differs at the 1e-13 level.
+#include "common.cuh"
+
+namespace cl {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBlocks = 592;
+constexpr int kQ1 = 8;    // pass-1 quantities per channel: {sw, svw, ssig, nsig} x {abs, rel}
+constexpr int kQ2 = 2;    // pass-2 quantities per channel: {abs, rel}
+
+struct PairArgs {
+    const double* x_val;
+    const double* x_std;
+    const double* y_val;
+    const double* y_std;
+    double multiplier;
+    double lower[CL_MAX_CHANNELS], upper[CL_MAX_CHANNELS];
+    int has_thr;
+    int64_t n;
+    int C;
+};
+
+struct Diff {
+    double a, r, sa, sr;     // absolute / relative difference and their uncertainties
+};
+
+__device__ __forceinline__ Diff difference(const PairArgs& p, int64_t i, int c, bool use_std) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double x = p.x_val[i], y = p.y_val[i];
+    double xs = p.x_std ? p.x_std[i] : 0.0, ys = p.y_std ? p.y_std[i] : 0.0;
+    if (p.has_thr) {                                     // apply_thresholds, measurand.py:418-428
+        if (x < p.lower[c] || x > p.upper[c]) { x = nan; if (p.x_std) xs = nan; }
+        if (y < p.lower[c] || y > p.upper[c]) { y = nan; if (p.y_std) ys = nan; }
+    }
+    Diff d;
+    const double scale = __dmul_rn(p.multiplier, y);     // measurand.py:634-636
+    d.a = __dsub_rn(x, scale);
+    d.r = __ddiv_rn(d.a, scale);
+    d.sa = d.sr = 0.0;
+    if (use_std) {                                       // :652-653
+        const double my = __dmul_rn(p.multiplier, ys);
+        d.sa = __dsqrt_rn(__dadd_rn(__dmul_rn(xs, xs), __dmul_rn(my, my)));
+        const double t1 = __ddiv_rn(xs, scale);
+        const double t2 = __ddiv_rn(__dmul_rn(ys, x), __dmul_rn(p.multiplier, __dmul_rn(y, y)));
+        d.sr = __dsqrt_rn(__dadd_rn(__dmul_rn(t1, t1), __dmul_rn(t2, t2)));
+    }
+    return d;
+}
+
+// Deterministic block reduction of per-thread accumulators: thread t owns channel (t % C) because
+// the grid stride is a multiple of C.  acc -> shared [Q][kThreads]; then Q*C threads sum their
+// column in index order.
+template <int Q>
+__device__ __forceinline__ void block_reduce(const double (&acc)[Q], int C, int lanes_used, double* out) {
+    __shared__ double sh[Q][kThreads];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) sh[q][threadIdx.x] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < Q * C) {
+        const int q = threadIdx.x / C, c = threadIdx.x % C;
+        double s = 0.0;
+        for (int t = c; t < lanes_used; t += C) s += sh[q][t];
+        out[q * C + c] = s;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ bool not_nan(double v) { return v == v; }
+
+template <bool USE_STD>
+__global__ void __launch_bounds__(kThreads)
+pair_pass1_kernel(const PairArgs p, double* __restrict__ partial /* [blocks][kQ1][C] */) {
+    const int C = p.C;
+    const int lanes_used = (kThreads / C) * C;               // threads beyond that idle: keeps t % C fixed
+    const int64_t stride = (int64_t)gridDim.x * lanes_used;
+    double acc[kQ1] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if ((int)threadIdx.x < lanes_used) {
+        const int c = threadIdx.x % C;                       // (block offset and stride are multiples of C)
+        for (int64_t i = (int64_t)blockIdx.x * lanes_used + threadIdx.x; i < p.n; i += stride) {
+            const Diff d = difference(p, i, c, USE_STD);
+            if (USE_STD) {
+                const double wa = __ddiv_rn(1.0, d.sa), wr = __ddiv_rn(1.0, d.sr);     // weights = 1 / stds
+                if (not_nan(wa)) acc[0] += wa;
+                const double va = __dmul_rn(d.a, wa);
+                if (not_nan(va)) acc[1] += va;
+                if (not_nan(d.sa)) { acc[2] += d.sa; acc[3] += 1.0; }
+                if (not_nan(wr)) acc[4] += wr;
+                const double vr = __dmul_rn(d.r, wr);
+                if (not_nan(vr)) acc[5] += vr;
+                if (not_nan(d.sr)) { acc[6] += d.sr; acc[7] += 1.0; }
+            } else {
+                if (not_nan(d.a)) { acc[0] += 1.0; acc[1] += d.a; }
+                if (not_nan(d.r)) { acc[4] += 1.0; acc[5] += d.r; }
+            }
+        }
+    }
+    block_reduce<kQ1>(acc, C, lanes_used, partial + (int64_t)blockIdx.x * kQ1 * C);
+}
+
+// means[q][c]: q = 0 abs mean, 1 rel mean (+ the pass-1 totals kept for the final kernel)
+__global__ void pair_means_kernel(const double* __restrict__ partial, int n_blocks, int C,
+                                  double* __restrict__ totals /* [kQ1][C] */, double* __restrict__ means /* [2][C] */) {
+    const int t = threadIdx.x;
+    if (t < kQ1 * C) {
+        double s = 0.0;
+        for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)b * kQ1 * C + t];
+        totals[t] = s;
+    }
+    __syncthreads();
+    if (t < 2 * C) {
+        const int which = t / C, c = t % C;                  // 0 = abs, 1 = rel
+        means[t] = totals[(which * 4 + 1) * C + c] / totals[(which * 4 + 0) * C + c];
+    }
+}
+
+template <bool USE_STD>
+__global__ void __launch_bounds__(kThreads)
+pair_pass2_kernel(const PairArgs p, const double* __restrict__ means, double* __restrict__ partial /* [blocks][kQ2][C] */) {
+    const int C = p.C;
+    const int lanes_used = (kThreads / C) * C;
+    const int64_t stride = (int64_t)gridDim.x * lanes_used;
+    double acc[kQ2] = {0, 0};
+    if ((int)threadIdx.x < lanes_used) {
+        const int c = threadIdx.x % C;
+        const double ma = means[c], mr = means[C + c];
+        for (int64_t i = (int64_t)blockIdx.x * lanes_used + threadIdx.x; i < p.n; i += stride) {
+            const Diff d = difference(p, i, c, USE_STD);
+            const double da = __dsub_rn(d.a, ma), dr = __dsub_rn(d.r, mr);
+            double ta = __dmul_rn(da, da), tr = __dmul_rn(dr, dr);
+            if (USE_STD) {
+                ta = __dmul_rn(__ddiv_rn(1.0, d.sa), ta);                      // weights * (values - mean)**2
+                tr = __dmul_rn(__ddiv_rn(1.0, d.sr), tr);
+            }
+            if (not_nan(ta)) acc[0] += ta;
+            if (not_nan(tr)) acc[1] += tr;
+        }
+    }
+    block_reduce<kQ2>(acc, C, lanes_used, partial + (int64_t)blockIdx.x * kQ2 * C);
+}
+
+// stats[which][k][c]: which 0 = absolute, 1 = relative; k 0 = mean, 1 = std, 2 = error
+__global__ void pair_final_kernel(const double* __restrict__ partial2, int n_blocks, int C, int use_std,
+                                  const double* __restrict__ totals, const double* __restrict__ means,
+                                  double* __restrict__ stats) {
+    const int t = threadIdx.x;
+    if (t >= 2 * C) return;
+    const int which = t / C, c = t % C;
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += partial2[(int64_t)b * kQ2 * C + t];
+    const double denom = totals[(which * 4 + 0) * C + c];                     // sum of weights / count
+    stats[(which * 3 + 0) * C + c] = means[t];
+    stats[(which * 3 + 1) * C + c] = sqrt(s / denom);
+    stats[(which * 3 + 2) * C + c] = use_std ? totals[(which * 4 + 2) * C + c] / totals[(which * 4 + 3) * C + c]
+                                             : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+}  // namespace
+}  // namespace cl
+
+extern "C" {
+
+size_t cl_pair_statistics_workspace_bytes(int channels) {
+    const size_t c = channels > 0 ? channels : 1;
+    return ((size_t)cl::kBlocks * (cl::kQ1 + cl::kQ2) * c + cl::kQ1 * c + 2 * c) * sizeof(double);
+}
+
+int cl_pair_statistics(const double* x_val, const double* x_std, const double* y_val, const double* y_std,
+                       double multiplier, const double* lower, const double* upper, int64_t n_samples,
+                       int channels, double* stats, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace cl;
+    CL_REQUIRE(n_samples >= 0 && channels >= 1 && channels <= CL_MAX_CHANNELS);
+    CL_REQUIRE(x_val && y_val && stats);
+    CL_REQUIRE(n_samples % channels == 0);
+    CL_REQUIRE((lower == nullptr) == (upper == nullptr));
+    if (!workspace || workspace_bytes < cl_pair_statistics_workspace_bytes(channels)) return CL_ERR_WORKSPACE;
+    PairArgs p;
+    p.x_val = x_val; p.x_std = x_std; p.y_val = y_val; p.y_std = y_std;
+    p.multiplier = multiplier; p.n = n_samples; p.C = channels;
+    p.has_thr = lower != nullptr;
+    for (int c = 0; c < CL_MAX_CHANNELS; ++c) {      // HOST arrays of per-channel limits
+        p.lower[c] = (lower && c < channels) ? lower[c] : 0.0;
+        p.upper[c] = (upper && c < channels) ? upper[c] : 0.0;
+    }
+    const bool use_std = x_std != nullptr || y_std != nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    double* partial1 = reinterpret_cast<double*>(workspace);
+    double* partial2 = partial1 + (size_t)kBlocks * kQ1 * channels;
+    double* totals = partial2 + (size_t)kBlocks * kQ2 * channels;
+    double* means = totals + (size_t)kQ1 * channels;
+    if (use_std) pair_pass1_kernel<true><<<kBlocks, kThreads, 0, s>>>(p, partial1);
+    else pair_pass1_kernel<false><<<kBlocks, kThreads, 0, s>>>(p, partial1);
+    int st = launched();
+    if (st != CL_OK) return st;
+    pair_means_kernel<<<1, 64, 0, s>>>(partial1, kBlocks, channels, totals, means);
+    if ((st = launched()) != CL_OK) return st;
+    if (use_std) pair_pass2_kernel<true><<<kBlocks, kThreads, 0, s>>>(p, means, partial2);
+    else pair_pass2_kernel<false><<<kBlocks, kThreads, 0, s>>>(p, means, partial2);
+    if ((st = launched()) != CL_OK) return st;
+    pair_final_kernel<<<1, 32, 0, s>>>(partial2, kBlocks, channels, use_std ? 1 : 0, totals, means, stats);
+    return launched();
+}
+
+}  // extern "C"

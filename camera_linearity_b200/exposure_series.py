@@ -44,6 +44,15 @@ class ExposurePair(object):
             self.absolute_difference = None
             self.relative_difference = None
 
+    def compute_pair_statistics(self, lower=None, upper=None):
+        """Fused GPU path of ``compute_difference`` + ``compute_stats(axis=(0, 1))`` (optionally with the
+        thresholds of ``apply_thresholds``): one kernel sequence, no difference images in HBM."""
+        x, y = self.short_exposure.measurand, self.long_exposure.measurand
+        stats = ops.pair_statistics(x.val, x.std, y.val, y.std, self.exposure_ratio, lower, upper)
+        use_std = x.std is not None or y.std is not None
+        self.absolute_stats = {"mean": stats[0, 0], "std": stats[0, 1], "error": stats[0, 2] if use_std else None}
+        self.relative_stats = {"mean": stats[1, 0], "std": stats[1, 1], "error": stats[1, 2] if use_std else None}
+
     def process_linearity_distribution(self, bins: int, included_range=None, channels=None, use_std=False):
         return (self.absolute_difference.measurand.compute_channel_histogram(bins, included_range, channels, use_std),
                 self.relative_difference.measurand.compute_channel_histogram(bins, included_range, channels, use_std))
@@ -218,9 +227,13 @@ class ExposureSeries(object):
             if image_set.measurand.std is None and use_std:
                 image_set.load_std_image()
             image_set.measurand.apply_thresholds(lower, upper)
+        fused = all(s.measurand.val.is_cuda and s.measurand.val.ndim == 3 for s in self.input_image_sets)
         for pair in self.exposure_pairs:
-            pair.compute_difference()
-            pair.compute_stats(axis=(0, 1), release_memory_after=True)
+            if fused:
+                pair.compute_pair_statistics()         # the inputs are already thresholded (NaN-marked)
+            else:
+                pair.compute_difference()
+                pair.compute_stats(axis=(0, 1), release_memory_after=True)
 
     def collect_exposure_pair_stats(self, return_cupy: Optional[bool] = False):
         keys = ('ratios', 'means', 'stds', 'errors')

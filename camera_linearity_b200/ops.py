@@ -453,6 +453,35 @@ class IcrfEnergyPlan:
         return self.finalize()
 
 
+# ------------------------------------------------------------------------------------- linearity
+def pair_statistics(x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor, y_std: Optional[Tensor],
+                    multiplier: float, lower: Optional[Sequence[Optional[float]]] = None,
+                    upper: Optional[Sequence[Optional[float]]] = None) -> Tensor:
+    """Fused thresholds -> scaled difference -> per-channel statistics over all leading axes of one
+    exposure pair (measurand.py:375-428, 620-655, 318-350).  Returns a (2, 3, C) tensor:
+    [absolute | relative] x [mean | std | error]."""
+    _require_cuda(x_val, x_std, y_val, y_std)
+    lib = _lib.load()
+    if x_val.shape != y_val.shape:
+        raise ValueError('Measurands are not broadcastable.')
+    c = int(x_val.shape[-1])
+    xv, xs, yv, ys = _f64c(x_val), _f64c(x_std), _f64c(y_val), _f64c(y_std)
+    lo = hi = None
+    if lower is not None or upper is not None:
+        lower = [None] * c if lower is None else list(lower)
+        upper = [None] * c if upper is None else list(upper)
+        if len(lower) != c or len(upper) != c:
+            raise ValueError("The length of 'lower' and 'upper' must match the size of the independent axis.")
+        lo = (C.c_double * c)(*[-float("inf") if v is None else float(v) for v in lower])
+        hi = (C.c_double * c)(*[float("inf") if v is None else float(v) for v in upper])
+    stats = torch.empty((2, 3, c), dtype=torch.float64, device=x_val.device)
+    ws_bytes = lib.cl_pair_statistics_workspace_bytes(c)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x_val.device)
+    check(lib.cl_pair_statistics(_ptr(xv), _ptr(xs), _ptr(yv), _ptr(ys), float(multiplier), lo, hi, xv.numel(), c,
+                                 _ptr(stats), _ptr(ws), ws_bytes, _stream()), "cl_pair_statistics")
+    return stats
+
+
 # ------------------------------------------------------------------------------------- custom ops
 # Registered for discoverability / composability with torch.library; they call the functions above.
 @torch.library.custom_op("camera_linearity::linearize", mutates_args=(), device_types="cuda")

@@ -206,6 +206,24 @@ int cl_icrf_energy_partial(const cl_icrf_problem* p, const void* tables,
 int cl_icrf_energy_finalize(const cl_icrf_problem* p, const double* pair_acc,
                             const int32_t* valid, double* energy /* device [S] */, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Linearity analysis of one exposure pair (first "next" row) -- replaces
+ * AbstractMeasurand.apply_thresholds (modules/measurand.py:375-428), compute_difference
+ * (:620-655) and compute_dimension_statistics(axis=(0,1)) (:318-350) as
+ * ExposureSeries.process_linearity chains them (modules/exposure_series.py:421-446).
+ *
+ *   a = x - m*y,  r = a / (m*y)  (+ first-order uncertainties when a std is given);
+ *   stats[which][k][c], which: 0 = absolute, 1 = relative; k: 0 = mean, 1 = std, 2 = error
+ *   (NaN-skipping; inverse-sigma weighted when any std is given, error = mean sigma, else NaN).
+ *   lower / upper: HOST arrays [C] of per-channel limits applied to x and y first (values outside
+ *   become NaN), or both NULL when the inputs are already thresholded.
+ * ------------------------------------------------------------------------------------------- */
+size_t cl_pair_statistics_workspace_bytes(int channels);
+int cl_pair_statistics(const double* x_val, const double* x_std, const double* y_val, const double* y_std,
+                       double multiplier, const double* lower, const double* upper, int64_t n_samples,
+                       int channels, double* stats /* device [2][3][C] */, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

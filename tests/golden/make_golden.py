@@ -324,6 +324,38 @@ def golden_energy(ref):
                         pairs_nostd=pairs_nostd, pairs_std=pairs_std)
 
 
+# ----------------------------------------------------------------------------- linearity chain
+def golden_linearity(ref):
+    # apply_thresholds -> ImageSet.compute_difference -> compute_dimension_statistics(axis=(0,1)),
+    # all UNMODIFIED reference code (exposure_series.py:421-446)
+    NM = ref.measurand.NumpyMeasurand
+    M = ref.measurand.AbstractMeasurand
+    rng = np.random.default_rng(51)
+    icrf, _ = icrf_tables(3, base=2.0, step=0.1)
+    t = (0.01, 0.04)
+    rad = rng.uniform(0, 1, (36, 44, 3)) * 30
+    dn = [np.rint(255 * np.clip(rad * tk, 0, 1) ** (1 / 2.2)).astype(np.uint8) for tk in t]
+    vals = [icrf[d, np.arange(3)] * (1 + rng.normal(0, 0.01, d.shape)) for d in dn]
+    stds = [rng.uniform(0.002, 0.02, d.shape) for d in dn]
+    lower = [float(icrf[5, c]) for c in range(3)]
+    upper = [float(icrf[250, c]) for c in range(3)]
+    out = dict(x_val=vals[0], y_val=vals[1], x_std=stds[0], y_std=stds[1], lower=np.array(lower),
+               upper=np.array(upper), multiplier=t[0] / t[1])
+    for tag, use_std in (("std", True), ("nostd", False)):
+        x = NM(vals[0].copy(), stds[0].copy() if use_std else None)
+        y = NM(vals[1].copy(), stds[1].copy() if use_std else None)
+        x.apply_thresholds(lower, upper)
+        y.apply_thresholds(lower, upper)
+        a, r = M.compute_difference(x, y, t[0] / t[1])
+        for name, m in (("abs", a), ("rel", r)):
+            st = m.compute_dimension_statistics(axis=(0, 1))
+            out[f"{tag}_{name}_mean"] = st["mean"]
+            out[f"{tag}_{name}_std"] = st["std"]
+            if st["error"] is not None:
+                out[f"{tag}_{name}_error"] = st["error"]
+    np.savez_compressed(OUT / 'k5_linearity.npz', **out)
+
+
 if __name__ == '__main__':
     import warnings
     warnings.simplefilter('ignore')
@@ -331,6 +363,7 @@ if __name__ == '__main__':
     golden_linearize(ref)
     golden_welford(ref)
     golden_energy(ref)
+    golden_linearity(ref)
     golden_merge()
     for f in sorted(OUT.glob('*.npz')):
         print(f.name, f.stat().st_size)

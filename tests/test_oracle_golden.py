@@ -181,3 +181,20 @@ def test_energy_survey_kat():
         assert oe.energy(p, mean, pca, dn, None, 5, 250, True, t) == e0
         assert oe.energy(p, mean, pca, dn, sd, 5, 250, True, t) == e1
     assert oe.energy(np.zeros(5), mean, pca, np.zeros_like(dn), None, 5, 250, True, t) == np.inf
+
+
+# ------------------------------------------------------------------ linearity chain (8f rank 1)
+def test_linearity_chain_matches_reference_bitexact(golden_dir):
+    from oracle import linearity as oli
+    g = _load(golden_dir, "k5_linearity.npz")
+    lower, upper = list(g["lower"]), list(g["upper"])
+    for tag, use_std in (("std", True), ("nostd", False)):
+        a, r = oli.pair_statistics(g["x_val"], g["x_std"] if use_std else None, g["y_val"],
+                                   g["y_std"] if use_std else None, float(g["multiplier"]), lower, upper)
+        for name, st in (("abs", a), ("rel", r)):
+            assert np.array_equal(st["mean"], g[f"{tag}_{name}_mean"])
+            assert np.array_equal(st["std"], g[f"{tag}_{name}_std"])
+            if use_std:
+                assert np.array_equal(st["error"], g[f"{tag}_{name}_error"])
+            else:
+                assert st["error"] is None
