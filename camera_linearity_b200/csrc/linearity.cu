@@ -18,7 +18,7 @@ namespace cl {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kBlocks = 592;
+constexpr int kBlocks = 444;  // 148 SMs x 3 resident CTAs; fixed (not sm_count) so the summation order is machine-independent
 constexpr int kQ1 = 8;    // pass-1 quantities per channel: {sw, svw, ssig, nsig} x {abs, rel}
 constexpr int kQ2 = 2;    // pass-2 quantities per channel: {abs, rel}
 
@@ -36,29 +36,94 @@ struct PairArgs {
 
 struct Diff {
     double a, r, sa, sr;     // absolute / relative difference and their uncertainties
+    double wa, wr;           // 1/sa, 1/sr
+    bool bad_v, bad_sa, bad_sr;   // the reference's value would be NaN here (thresholded or NaN input)
 };
 
-__device__ __forceinline__ Diff difference(const PairArgs& p, int64_t i, int c, bool use_std) {
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    double x = p.x_val[i], y = p.y_val[i];
-    double xs = p.x_std ? p.x_std[i] : 0.0, ys = p.y_std ? p.y_std[i] : 0.0;
-    if (p.has_thr) {                                     // apply_thresholds, measurand.py:418-428
-        if (x < p.lower[c] || x > p.upper[c]) { x = nan; if (p.x_std) xs = nan; }
-        if (y < p.lower[c] || y > p.upper[c]) { y = nan; if (p.y_std) ys = nan; }
-    }
+struct Raw {
+    double x, y, xs, ys;
+};
+
+constexpr int kUnroll = 4;   // independent samples in flight per thread (the loads of all of them issue first)
+
+__device__ __forceinline__ Raw load_raw(const PairArgs& p, int64_t i) {
+    Raw r;
+    r.x = __ldcs(p.x_val + i);
+    r.y = __ldcs(p.y_val + i);
+    r.xs = p.x_std ? __ldcs(p.x_std + i) : 0.0;
+    r.ys = p.y_std ? __ldcs(p.y_std + i) : 0.0;
+    return r;
+}
+
+__device__ __forceinline__ Diff difference(const PairArgs& p, const Raw& raw, double lo, double hi, bool use_std) {
+    double x = raw.x, y = raw.y, xs = raw.xs, ys = raw.ys;
+    // apply_thresholds (measurand.py:418-428) turns out-of-range values and their std into NaN.  NaN
+    // samples would send every lane's rcp / rsqrt through its slow path, so the NaN-ness is carried in
+    // flags (exactly where IEEE propagation would put it) and the arithmetic runs on 1.0 instead.
+    const bool tx = p.has_thr && (x < lo || x > hi), ty = p.has_thr && (y < lo || y > hi);
+    const bool nx = tx || x != x, ny = ty || y != y;
+    const bool nxs = (tx && p.x_std) || xs != xs, nys = (ty && p.y_std) || ys != ys;
+    x = nx ? 1.0 : x;  y = ny ? 1.0 : y;  xs = nxs ? 1.0 : xs;  ys = nys ? 1.0 : ys;
     Diff d;
+    // One reciprocal and two reciprocal square roots replace the reference's five divisions and two
+    // square roots (a/s = a*(1/s), 1/sqrt(q) = rsqrt(q), sqrt(q) = q*rsqrt(q)): each element moves by
+    // <= 2 ulp, far inside the reduction's own reordering error, and the 0 / inf cases match.
     const double scale = __dmul_rn(p.multiplier, y);     // measurand.py:634-636
+    const double inv = __drcp_rn(scale);
     d.a = __dsub_rn(x, scale);
-    d.r = __ddiv_rn(d.a, scale);
-    d.sa = d.sr = 0.0;
+    d.r = __dmul_rn(d.a, inv);
+    d.bad_v = nx || ny;
+    d.sa = d.sr = d.wa = d.wr = 0.0;
+    d.bad_sa = d.bad_sr = false;
     if (use_std) {                                       // :652-653
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
         const double my = __dmul_rn(p.multiplier, ys);
-        d.sa = __dsqrt_rn(__dadd_rn(__dmul_rn(xs, xs), __dmul_rn(my, my)));
-        const double t1 = __ddiv_rn(xs, scale);
-        const double t2 = __ddiv_rn(__dmul_rn(ys, x), __dmul_rn(p.multiplier, __dmul_rn(y, y)));
-        d.sr = __dsqrt_rn(__dadd_rn(__dmul_rn(t1, t1), __dmul_rn(t2, t2)));
+        const double qa = __dadd_rn(__dmul_rn(xs, xs), __dmul_rn(my, my));
+        d.wa = rsqrt(qa);                                // weights = 1 / stds
+        d.sa = (qa > 0.0 && qa < inf) ? __dmul_rn(qa, d.wa) : qa;
+        const double t1 = __dmul_rn(xs, inv);
+        const double t2 = __dmul_rn(__dmul_rn(__dmul_rn(ys, x), inv), __dmul_rn(inv, p.multiplier));   // ys*x / (m*y*y)
+        const double qr = __dadd_rn(__dmul_rn(t1, t1), __dmul_rn(t2, t2));
+        d.wr = rsqrt(qr);
+        d.sr = (qr > 0.0 && qr < inf) ? __dmul_rn(qr, d.wr) : qr;
+        d.bad_sa = nxs || nys;
+        d.bad_sr = nxs || nys || nx || ny;
     }
     return d;
+}
+
+__device__ __forceinline__ bool not_nan(double v) { return v == v; }
+
+// np.nansum semantics: every term is skipped individually when it is NaN.
+template <bool USE_STD>
+__device__ __forceinline__ void accumulate1(double (&acc)[8], const Diff& d) {
+    if (USE_STD) {
+        const double va = __dmul_rn(d.a, d.wa), vr = __dmul_rn(d.r, d.wr);
+        if (!d.bad_sa && not_nan(d.wa)) acc[0] += d.wa;
+        if (!d.bad_sa && !d.bad_v && not_nan(va)) acc[1] += va;
+        if (!d.bad_sa && not_nan(d.sa)) { acc[2] += d.sa; acc[3] += 1.0; }
+        if (!d.bad_sr && not_nan(d.wr)) acc[4] += d.wr;
+        if (!d.bad_sr && not_nan(vr)) acc[5] += vr;            // (bad_sr includes bad_v)
+        if (!d.bad_sr && not_nan(d.sr)) { acc[6] += d.sr; acc[7] += 1.0; }
+    } else {
+        if (!d.bad_v && not_nan(d.a)) { acc[0] += 1.0; acc[1] += d.a; }
+        if (!d.bad_v && not_nan(d.r)) { acc[4] += 1.0; acc[5] += d.r; }
+    }
+}
+
+template <bool USE_STD>
+__device__ __forceinline__ void accumulate2(double (&acc)[2], const Diff& d, double ma, double mr) {
+    const double da = __dsub_rn(d.a, ma), dr = __dsub_rn(d.r, mr);
+    double ta = __dmul_rn(da, da), tr = __dmul_rn(dr, dr);
+    bool bad_a = d.bad_v, bad_r = d.bad_v;
+    if (USE_STD) {
+        ta = __dmul_rn(d.wa, ta);                                      // weights * (values - mean)**2
+        tr = __dmul_rn(d.wr, tr);
+        bad_a = bad_a || d.bad_sa;
+        bad_r = d.bad_sr;
+    }
+    if (!bad_a && not_nan(ta)) acc[0] += ta;
+    if (!bad_r && not_nan(tr)) acc[1] += tr;
 }
 
 // Deterministic block reduction of per-thread accumulators: thread t owns channel (t % C) because
@@ -79,10 +144,8 @@ __device__ __forceinline__ void block_reduce(const double (&acc)[Q], int C, int 
     __syncthreads();
 }
 
-__device__ __forceinline__ bool not_nan(double v) { return v == v; }
-
 template <bool USE_STD>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 pair_pass1_kernel(const PairArgs p, double* __restrict__ partial /* [blocks][kQ1][C] */) {
     const int C = p.C;
     const int lanes_used = (kThreads / C) * C;               // threads beyond that idle: keeps t % C fixed
@@ -90,23 +153,16 @@ pair_pass1_kernel(const PairArgs p, double* __restrict__ partial /* [blocks][kQ1
     double acc[kQ1] = {0, 0, 0, 0, 0, 0, 0, 0};
     if ((int)threadIdx.x < lanes_used) {
         const int c = threadIdx.x % C;                       // (block offset and stride are multiples of C)
-        for (int64_t i = (int64_t)blockIdx.x * lanes_used + threadIdx.x; i < p.n; i += stride) {
-            const Diff d = difference(p, i, c, USE_STD);
-            if (USE_STD) {
-                const double wa = __ddiv_rn(1.0, d.sa), wr = __ddiv_rn(1.0, d.sr);     // weights = 1 / stds
-                if (not_nan(wa)) acc[0] += wa;
-                const double va = __dmul_rn(d.a, wa);
-                if (not_nan(va)) acc[1] += va;
-                if (not_nan(d.sa)) { acc[2] += d.sa; acc[3] += 1.0; }
-                if (not_nan(wr)) acc[4] += wr;
-                const double vr = __dmul_rn(d.r, wr);
-                if (not_nan(vr)) acc[5] += vr;
-                if (not_nan(d.sr)) { acc[6] += d.sr; acc[7] += 1.0; }
-            } else {
-                if (not_nan(d.a)) { acc[0] += 1.0; acc[1] += d.a; }
-                if (not_nan(d.r)) { acc[4] += 1.0; acc[5] += d.r; }
-            }
+        const double lo = p.lower[c], hi = p.upper[c];
+        int64_t i = (int64_t)blockIdx.x * lanes_used + threadIdx.x;
+        for (; i + (kUnroll - 1) * stride < p.n; i += kUnroll * stride) {
+            Raw raw[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) raw[u] = load_raw(p, i + u * stride);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) accumulate1<USE_STD>(acc, difference(p, raw[u], lo, hi, USE_STD));
         }
+        for (; i < p.n; i += stride) accumulate1<USE_STD>(acc, difference(p, load_raw(p, i), lo, hi, USE_STD));
     }
     block_reduce<kQ1>(acc, C, lanes_used, partial + (int64_t)blockIdx.x * kQ1 * C);
 }
@@ -128,7 +184,7 @@ __global__ void pair_means_kernel(const double* __restrict__ partial, int n_bloc
 }
 
 template <bool USE_STD>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 pair_pass2_kernel(const PairArgs p, const double* __restrict__ means, double* __restrict__ partial /* [blocks][kQ2][C] */) {
     const int C = p.C;
     const int lanes_used = (kThreads / C) * C;
@@ -137,17 +193,16 @@ pair_pass2_kernel(const PairArgs p, const double* __restrict__ means, double* __
     if ((int)threadIdx.x < lanes_used) {
         const int c = threadIdx.x % C;
         const double ma = means[c], mr = means[C + c];
-        for (int64_t i = (int64_t)blockIdx.x * lanes_used + threadIdx.x; i < p.n; i += stride) {
-            const Diff d = difference(p, i, c, USE_STD);
-            const double da = __dsub_rn(d.a, ma), dr = __dsub_rn(d.r, mr);
-            double ta = __dmul_rn(da, da), tr = __dmul_rn(dr, dr);
-            if (USE_STD) {
-                ta = __dmul_rn(__ddiv_rn(1.0, d.sa), ta);                      // weights * (values - mean)**2
-                tr = __dmul_rn(__ddiv_rn(1.0, d.sr), tr);
-            }
-            if (not_nan(ta)) acc[0] += ta;
-            if (not_nan(tr)) acc[1] += tr;
+        const double lo = p.lower[c], hi = p.upper[c];
+        int64_t i = (int64_t)blockIdx.x * lanes_used + threadIdx.x;
+        for (; i + (kUnroll - 1) * stride < p.n; i += kUnroll * stride) {
+            Raw raw[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) raw[u] = load_raw(p, i + u * stride);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) accumulate2<USE_STD>(acc, difference(p, raw[u], lo, hi, USE_STD), ma, mr);
         }
+        for (; i < p.n; i += stride) accumulate2<USE_STD>(acc, difference(p, load_raw(p, i), lo, hi, USE_STD), ma, mr);
     }
     block_reduce<kQ2>(acc, C, lanes_used, partial + (int64_t)blockIdx.x * kQ2 * C);
 }

@@ -45,7 +45,7 @@ def main():
     if len(rows) > 2:
         h = rows[1]
         ix = {name: i for i, name in enumerate(h)}
-        data = [r for r in rows[2:] if len(r) == len(h)]
+        data = [r for r in rows[2:] if len(r) == len(h) and r[ix["# Samples"]].isdigit()]   # (headers repeat per kernel)
         tot = sum(int(r[ix["# Samples"]]) for r in data) or 1
         lines.append(f"top stall sites (of {tot} samples, {len(data)} SASS instructions):")
         for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]]))[:15]:
