@@ -237,54 +237,92 @@ __device__ __forceinline__ void file_hit(const MergeParams& p, int k, uint32_t s
     const uint32_t px = sample / 3u, c = sample - px * 3u;
     const uint32_t tile = px / kStagedTilePx;
     if ((int)tile >= p.n_full_tiles) return;            // ragged tail: the generic kernel repairs inline
-    uint32_t* bucket = p.buckets + (size_t)tile * kBucketWords;
-    const uint32_t slot = atomicAdd(bucket, 1u);
+    const uint32_t slot = atomicAdd(p.bucket_counts + (size_t)tile * 4, 1u);
     if (slot < (uint32_t)kBucketCap) {
-        bucket[4 + 4 * slot] = (px - tile * kStagedTilePx) | (c << 9) | ((uint32_t)k << 11);
+        p.bucket_entries[((size_t)tile * kBucketCap + slot) * 4] =
+            (px - tile * kStagedTilePx) | (c << 9) | ((uint32_t)k << 11);
     } else {
         const uint32_t g = atomicAdd(&p.hot_list[0], 1u);
         if (g < p.hot_cap) p.hot_list[kHotListHeader + g] = sample;
     }
 }
 
+// byte >= thr for the four bytes of x, flagged in bit 7 of each byte (SWAR; __vcmpgeu4 is emulated):
+//   thr <= 128: b7 | carry((b & 0x7f) + 128 - thr)      thr > 128: b7 & carry((b & 0x7f) + 256 - thr)
+__device__ __forceinline__ uint32_t bytes_ge(uint32_t x, uint32_t add, bool low) {
+    const uint32_t lo = (x & 0x7f7f7f7fu) + add;
+    return (low ? (x | lo) : (x & lo)) & 0x80808080u;
+}
+
+// Work unit = (dark frame j, run of kScanThreads * kScanVecs 16-byte vectors); the units of all frames
+// form one flat list that the (exactly one wave of) blocks stride over, so no wave is part-empty.
+// Hits are parked in a shared-memory list (a shared atomic, ~100 cycles) and filed into the global
+// buckets once per block at the end: a global atomic inside the streaming loop costs ~1.5 us of
+// latency per unit for every warp that sees a hit, which is most of them.
+constexpr int kScanListCap = 2048;       // {sample, exposure} pairs per block; overflow files directly
+
 __global__ void __launch_bounds__(kScanThreads)
 dark_scan_kernel(const __grid_constant__ MergeParams p) {
+    __shared__ uint2 hits[kScanListCap];
+    __shared__ uint32_t n_hits;
+    if (threadIdx.x == 0) n_hits = 0;
+    __syncthreads();
+    auto park = [&](int k, uint32_t sample) {
+        const uint32_t slot = atomicAdd(&n_hits, 1u);
+        if (slot < (uint32_t)kScanListCap) hits[slot] = make_uint2(sample, (uint32_t)k);
+        else file_hit(p, k, sample);
+    };
+    // 32-bit index arithmetic throughout: the staged path requires fewer than 2^32 samples
     const int64_t n = (int64_t)p.H * p.W * p.C;
-    const int64_t n_vec = (n + 15) / 16;        // the last vector may be ragged
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int k = 0; k < p.n; ++k) {
-        if (!p.dark[k] || p.hot_dn[k] > 255u) continue;
-        const uint32_t thr = p.hot_dn[k] * 0x01010101u;
-        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(p.dark[k]);
-        const uint4* src = reinterpret_cast<const uint4*>(bytes);
-        for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n_vec; base += stride * kScanVecs) {
-            uint4 q[kScanVecs];
+    const uint32_t n_vec = (uint32_t)(n / 16);  // full 16-byte vectors per dark frame
+    constexpr uint32_t kUnitVecs = kScanThreads * kScanVecs;
+    const uint32_t units_per_frame = (n_vec + kUnitVecs - 1) / kUnitVecs;
+    const uint32_t total = units_per_frame * (uint32_t)p.n_dark;
+    for (uint32_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+        const uint32_t j = unit / units_per_frame;
+        const uint32_t base = (unit - j * units_per_frame) * kUnitVecs + threadIdx.x;
+        const int k = p.dark_k[j];
+        const uint4* src = reinterpret_cast<const uint4*>(p.dark[k]);
+        const uint32_t thr = p.hot_dn[k];
+        const bool low = thr <= 128u;
+        const uint32_t add = (low ? 128u - thr : 256u - thr) * 0x01010101u;
+        uint4 q[kScanVecs];
 #pragma unroll
-            for (int u = 0; u < kScanVecs; ++u) {
-                const int64_t v = base + threadIdx.x + u * stride;
-                q[u] = (v * 16 + 16 <= n) ? __ldg(src + v) : make_uint4(0, 0, 0, 0);
-            }
+        for (int u = 0; u < kScanVecs; ++u) {
+            const uint32_t v = base + u * kScanThreads;
+            q[u] = v < n_vec ? __ldg(src + v) : make_uint4(0, 0, 0, 0);     // (zeros never reach a threshold >= 1 ...
+        }
 #pragma unroll
-            for (int u = 0; u < kScanVecs; ++u) {
-                const int64_t v = base + threadIdx.x + u * stride;
-                if (v * 16 + 16 <= n) {
-                    const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+        for (int u = 0; u < kScanVecs; ++u) {
+            const uint32_t v = base + u * kScanThreads;
+            const uint32_t h[4] = {bytes_ge(q[u].x, add, low), bytes_ge(q[u].y, add, low),
+                                   bytes_ge(q[u].z, add, low), bytes_ge(q[u].w, add, low)};
+            if ((h[0] | h[1] | h[2] | h[3]) == 0u || v >= n_vec) continue;  // ... and threshold 0 is caught here)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t m = __vcmpgeu4(w[j], thr);
-                        while (m) {
-                            const int b = (__ffs(m) - 1) >> 3;
-                            file_hit(p, k, (uint32_t)(v * 16 + j * 4 + b));
-                            m &= ~(0xFFu << (8 * b));
-                        }
-                    }
-                } else if (v < n_vec) {           // ragged last vector
-                    for (int64_t i = v * 16; i < n; ++i)
-                        if (bytes[i] >= p.hot_dn[k]) file_hit(p, k, (uint32_t)i);
+            for (int w = 0; w < 4; ++w) {
+                uint32_t m = h[w];
+                while (m) {
+                    const int b = (__ffs(m) - 1) >> 3;
+                    park(k, v * 16 + w * 4 + b);
+                    m &= m - 1;
                 }
             }
         }
     }
+    // ragged last (n % 16) bytes of every dark frame: a handful of bytes, filed directly by block 0
+    // (kept out of the park() path: a second call site there doubled the kernel's run time)
+    const uint32_t rag = (uint32_t)(n - (int64_t)n_vec * 16);
+    if (blockIdx.x == 0 && rag != 0u) {
+        for (uint32_t t = threadIdx.x; t < rag * (uint32_t)p.n_dark; t += kScanThreads) {
+            const uint32_t jr = t / rag;
+            const uint32_t i = n_vec * 16u + (t - jr * rag);
+            const int k = p.dark_k[jr];
+            if (reinterpret_cast<const uint8_t*>(p.dark[k])[i] >= p.hot_dn[k]) file_hit(p, k, i);
+        }
+    }
+    __syncthreads();
+    const uint32_t parked = min(n_hits, (uint32_t)kScanListCap);
+    for (uint32_t e = threadIdx.x; e < parked; e += kScanThreads) file_hit(p, (int)hits[e].y, hits[e].x);
 }
 
 // Full recomputation of one sample with the bad-pixel repair, same arithmetic (and the same
@@ -359,29 +397,67 @@ merge_fixup_kernel(const __grid_constant__ MergeParams p) {
 // ---- ROI means ------------------------------------------------------------------------------------
 constexpr int kRoiThreads = 256;
 
-__global__ void roi_partial_kernel(const void* __restrict__ flat, int flat_bytes, double max_dn,
-                                   const double* __restrict__ flat_std, int W, int C, int r0, int c0,
-                                   int rh, int rw, double* __restrict__ partial) {
+// CT = compile-time channel count (keeps the accumulators in registers); CT == 0: run-time C <= 8.
+// All kRoiBlocks blocks are resident at once (one wave) and every thread keeps four pixels in flight.
+template <int CT>
+__global__ void __launch_bounds__(kRoiThreads, CT ? 3 : 1)
+roi_partial_kernel(const void* __restrict__ flat, int flat_bytes, double max_dn,
+                   const double* __restrict__ flat_std, int W, int C_rt, int r0, int c0, int rh, int rw,
+                   double* __restrict__ partial) {
     // block b reduces ROI pixels [b*chunk, (b+1)*chunk) for every channel, fixed order
-    __shared__ double red[kRoiThreads / 32][2 * CL_MAX_CHANNELS];
+    constexpr int CM = CT ? CT : CL_MAX_CHANNELS;
+    constexpr int kPix = 4;
+    const int C = CT ? CT : C_rt;
+    __shared__ double red[kRoiThreads / 32][2 * CM];
     const int64_t npx = (int64_t)rh * rw;
     const int64_t chunk = (npx + gridDim.x - 1) / gridDim.x;
     const int64_t lo = (int64_t)blockIdx.x * chunk;
     const int64_t hi = lo + chunk < npx ? lo + chunk : npx;
-    double acc[2 * CL_MAX_CHANNELS];
-    for (int c = 0; c < 2 * C; ++c) acc[c] = 0.0;
-    for (int64_t q = lo + threadIdx.x; q < hi; q += blockDim.x) {
-        const int y = r0 + (int)(q / rw), x = c0 + (int)(q % rw);
-        const int64_t i = ((int64_t)y * W + x) * C;
-        for (int c = 0; c < C; ++c) {
-            acc[c] += flat_value(flat, flat_bytes, i + c, max_dn);
-            acc[C + c] += flat_std[i + c];
+    double acc[2 * CM];
+#pragma unroll
+    for (int c = 0; c < 2 * CM; ++c) acc[c] = 0.0;
+    for (int64_t q0 = lo + threadIdx.x; q0 < hi; q0 += (int64_t)kPix * kRoiThreads) {
+        double f[kPix][CM], sd[kPix][CM];
+#pragma unroll
+        for (int u = 0; u < kPix; ++u) {
+            const int64_t q = q0 + (int64_t)u * kRoiThreads;
+            const bool on = q < hi;
+            int64_t i = 0;
+            if (on) {
+                int64_t y, x;
+                if (npx < ((int64_t)1 << 31)) {          // 32-bit divide when it fits (the common case)
+                    const uint32_t yy = (uint32_t)q / (uint32_t)rw;
+                    y = yy; x = (uint32_t)q - yy * (uint32_t)rw;
+                } else {
+                    y = q / rw; x = q - y * rw;
+                }
+                i = ((r0 + y) * W + (c0 + x)) * C;
+            }
+#pragma unroll
+            for (int c = 0; c < CM; ++c) {
+                const bool live = on && c < C;
+                f[u][c] = live ? flat_value(flat, flat_bytes, i + c, max_dn) : 0.0;
+                sd[u][c] = live ? flat_std[i + c] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kPix; ++u) {                 // pixel order q0, q0 + 256, ... as a one-pixel loop would
+            if (q0 + (int64_t)u * kRoiThreads >= hi) break;
+#pragma unroll
+            for (int c = 0; c < CM; ++c) {
+                if (c >= C) break;
+                acc[c] += f[u][c];
+                acc[CM + c] += sd[u][c];
+            }
         }
     }
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    for (int c = 0; c < 2 * C; ++c) {
+#pragma unroll
+    for (int c = 0; c < 2 * CM; ++c) {                   // acc = [mean sums x CM | std sums x CM], red = [C | C]
+        const int cc = c < CM ? c : c - CM;
+        if (cc >= C) continue;
         const double v = warp_sum(acc[c]);
-        if (lane == 0) red[warp][c] = v;
+        if (lane == 0) red[warp][c < CM ? cc : C + cc] = v;
     }
     __syncthreads();
     if (threadIdx.x < 2 * C) {
@@ -397,12 +473,13 @@ __global__ void roi_final_kernel(const double* __restrict__ partial, int n_block
     const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (c >= 2 * C) return;
     double s = 0.0;
+#pragma unroll 8
     for (int b = lane; b < n_blocks; b += 32) s += partial[(int64_t)b * 2 * C + c];
     s = warp_sum(s);
     if (lane == 0) out[c] = s / count;
 }
 
-constexpr int kRoiBlocks = 592;
+constexpr int kRoiBlocks = 444;      // 148 SMs x 3 resident blocks; fixed so the summation order is machine-independent
 
 // ---- stand-alone Measurand kernels ------------------------------------------------------------------
 __global__ void gaussian_weight_kernel(const double* __restrict__ val, double* __restrict__ w,
@@ -479,12 +556,19 @@ int launch_merge_generic_range(const MergeParams& p, int64_t first_item, cudaStr
 }
 
 int launch_dark_scan(const MergeParams& p, cudaStream_t stream) {
-    cudaError_t e = cudaMemsetAsync(p.hot_list, 0, kHotListHeader * sizeof(uint32_t), stream);
+    // bucket counts and the hot-list counter are contiguous: one linear memset
+    cudaError_t e = cudaMemsetAsync(p.bucket_counts, 0,
+                                    ((size_t)p.n_full_tiles * 4 + kHotListHeader) * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return cuda_status(e);
-    // zero the 16-byte header (count) of every tile bucket
-    e = cudaMemset2DAsync(p.buckets, kBucketWords * sizeof(uint32_t), 0, 16, (size_t)p.n_full_tiles, stream);
-    if (e != cudaSuccess) return cuda_status(e);
-    dark_scan_kernel<<<sm_count() * 8, kScanThreads, 0, stream>>>(p);
+    static int per_sm = 0;               // resident blocks per SM: the grid is exactly one wave
+    if (per_sm == 0) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dark_scan_kernel, kScanThreads, 0) != cudaSuccess ||
+            occ < 1)
+            occ = 4;
+        per_sm = occ;
+    }
+    dark_scan_kernel<<<sm_count() * per_sm, kScanThreads, 0, stream>>>(p);
     return launched();
 }
 
@@ -577,6 +661,7 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
                 if (v > a->dark_threshold) { p.hot_dn[k] = d; break; }
             }
             p.any_dark = 1;
+            if (p.hot_dn[k] <= top) p.dark_k[p.n_dark++] = (uint8_t)k;
         }
     }
 
@@ -602,10 +687,12 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
         const size_t list_bytes = ((kHotListHeader + entries) * sizeof(uint32_t) + 15) / 16 * 16;
         const size_t bkt_bytes = (bucket_bytes((int64_t)p.H * p.W) + 15) / 16 * 16;
         if (workspace && aligned(workspace, 16) && workspace_bytes >= off + list_bytes + bkt_bytes) {
-            p.hot_list = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + off);
-            p.hot_cap = (uint32_t)entries;
-            p.buckets = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + off + list_bytes);
+            // [bucket counts][hot-list header + entries][bucket entries]
             p.n_full_tiles = (int32_t)(((int64_t)p.H * p.W) / kStagedTilePx);
+            p.bucket_counts = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + off);
+            p.hot_list = p.bucket_counts + (size_t)p.n_full_tiles * 4;
+            p.hot_cap = (uint32_t)entries;
+            p.bucket_entries = p.hot_list + list_bytes / sizeof(uint32_t);
         } else if (a->algo == 2) {
             return CL_ERR_WORKSPACE;
         }
@@ -644,9 +731,9 @@ int cl_flat_roi_means(const void* flat, int flat_bytes, double max_dn, const dou
     cudaStream_t s = (cudaStream_t)stream;
     double* partial = reinterpret_cast<double*>(workspace);
     // an empty ROI yields 0/0 = NaN, like np.mean of an empty slice
-    roi_partial_kernel<<<kRoiBlocks, kRoiThreads, 0, s>>>(flat, flat_bytes, max_dn, flat_std, width,
-                                                         channels, r0, c0, rw > 0 ? rh : 0,
-                                                         rw > 0 ? rw : 1, partial);
+    auto partial_kernel = channels == 3 ? roi_partial_kernel<3> : channels == 1 ? roi_partial_kernel<1> : roi_partial_kernel<0>;
+    partial_kernel<<<kRoiBlocks, kRoiThreads, 0, s>>>(flat, flat_bytes, max_dn, flat_std, width, channels, r0, c0,
+                                                     rw > 0 ? rh : 0, rw > 0 ? rw : 1, partial);
     int st = launched();
     if (st != CL_OK) return st;
     roi_final_kernel<<<1, 64 * CL_MAX_CHANNELS, 0, s>>>(partial, kRoiBlocks, channels, (double)rh * (double)rw,

@@ -35,14 +35,19 @@ struct MergeParams {
     uint32_t* hot_list;
     uint32_t hot_cap;
     int32_t n_full_tiles;      // 512-pixel tiles handled by the staged kernel
-    // per-tile bad-pixel patch buckets (staged path): [count, pad x3][kBucketCap x {meta, pad, sigma}]
-    uint32_t* buckets;
+    // per-tile bad-pixel patch buckets (staged path): counts [tile]{count, pad x3} sit right in front of
+    // the hot-list header (one memset clears both), entries [tile][kBucketCap]{meta, pad, sigma}
+    uint32_t* bucket_counts;
+    uint32_t* bucket_entries;
+    // exposures whose dark frame can flag a bad pixel (dark[k] set and hot_dn[k] <= max DN), in order
+    int32_t n_dark;
+    uint8_t dark_k[CL_MAX_EXPOSURES];
 };
 
 constexpr size_t kHotListHeader = 4;   // uint32 entries reserved in front of the list (counter + pad)
 constexpr int kStagedTilePx = 512;     // pixels per tile of the staged kernel
 constexpr int kBucketCap = 32;         // patch entries per tile; more -> the sample goes to the fix-up list
-constexpr int kBucketWords = 4 + 4 * kBucketCap;   // uint32 words per bucket (528 bytes)
+constexpr int kBucketWords = 4 + 4 * kBucketCap;   // uint32 words per bucket in shared memory: count block + entries (528 bytes)
 // entry meta word: pixel-in-tile [0,9) | channel [9,11) | exposure [11,16)
 
 // One exposure's contribution for one sample.  With S = sum of weights and rS = 1/S:

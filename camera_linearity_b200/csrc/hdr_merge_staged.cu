@@ -179,9 +179,11 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
                 mbar_wait(a_empty, (ti & 1) ^ 1);
                 mbar_expect_tx(a_full, (uint32_t)(p.n + (flat_u8 ? 1 : 0)) * kDnChunk +
                                            (patched ? kBucketWords * 4u : 0u));
-                if (patched)
-                    bulk_g2s(smem + L.off_bucket, p.buckets + (size_t)tile * kBucketWords, kBucketWords * 4,
-                             a_full);
+                if (patched) {          // count block (16 B) + entries (512 B) land back to back
+                    bulk_g2s(smem + L.off_bucket, p.bucket_counts + (size_t)tile * 4, 16, a_full);
+                    bulk_g2s(smem + L.off_bucket + 16, p.bucket_entries + (size_t)tile * kBucketCap * 4,
+                             kBucketCap * 16, a_full);
+                }
                 for (int k = 0; k < p.n; ++k)
                     bulk_g2s(abuf_dn + k * kDnChunk, reinterpret_cast<const uint8_t*>(p.dn[k]) + off,
                              kDnChunk, a_full);
@@ -363,7 +365,7 @@ bool make_layout(const MergeParams& p, StagedLayout& L) {
 bool merge_staged_supported(const MergeParams& p, bool all_std_images) {
     if (p.C != kC || p.bits != 256 || p.max_dn != 255.0 || !all_std_images) return false;
     if ((int64_t)p.H * p.W < kTilePx || (int64_t)p.H * p.W * kC >= 0xFFFFFFFFll) return false;
-    if (p.any_dark && (!p.hot_list || p.hot_cap == 0 || !p.buckets)) return false;
+    if (p.any_dark && (!p.hot_list || p.hot_cap == 0 || !p.bucket_counts || !p.bucket_entries)) return false;
     if (p.flat_bytes && (!aligned(p.flat_std, 16) || !aligned(p.flat, 16))) return false;
     StagedLayout L;
     return make_layout(p, L);

@@ -1,0 +1,40 @@
+"""Run ops.hdr_merge on the cfg2 bench stack a few times (profiling target for ncu).
+
+    python tools/run_merge.py [dark_threshold] [reps]
+"""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+import camera_linearity_b200 as cl  # noqa: E402
+from camera_linearity_b200 import ops  # noqa: E402
+
+
+def main():
+    thr = float(sys.argv[1]) if len(sys.argv) > 1 else bench.DARK_THRESHOLD
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    dev = torch.device("cuda:0")
+    wl = bench.WORKLOADS["cfg2"]
+    data = bench.make_stack_device(wl, 1234, dev)
+    icrf_np, diff_np = bench.icrf_tables(wl["C"])
+    icrf, diff = torch.from_numpy(icrf_np).to(dev), torch.from_numpy(diff_np).to(dev)
+    t = [float(x) for x in data["t"]]
+    roi = cl.measurand._flat_roi()
+    means = ops.flat_roi_means(data["flat"], data["flat_std"], roi)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for r in range(reps):
+        out = ops.hdr_merge(data["dn"], data["std"], t, icrf, diff, darks=data["darks"], dark_threshold=thr,
+                            median_kernel=bench.KERNEL, flat=data["flat"], flat_std=data["flat_std"],
+                            flat_means=means)
+        ev[r + 1].record()
+    torch.cuda.synchronize()
+    print("threshold", thr, "ms per call:", [round(ev[r].elapsed_time(ev[r + 1]), 4) for r in range(reps)])
+
+
+if __name__ == "__main__":
+    main()
