@@ -23,6 +23,20 @@ from .measurand import Measurand
 from .settings import GlobalSettings as gs
 
 
+def _quantize_8bit(x) -> np.ndarray:
+    """image_set.py:343-350: max-normalise (only when amax > 1), scale by MAX_DN, round half-even, uint8.
+    Device tensors are quantised by the CUDA kernel and cross PCIe as bytes; host arrays (GlobalSettings
+    DEVICE == 'cpu', used by the host-logic tests) follow the same formula in NumPy."""
+    if isinstance(x, torch.Tensor) and x.is_cuda:
+        from . import ops
+        return ops.quantize_8bit(x, gs.MAX_DN).cpu().numpy()
+    val = np.array(x.cpu().numpy() if isinstance(x, torch.Tensor) else x, dtype=np.float64, copy=True)
+    max_float = np.amax(val)
+    if max_float > 1:
+        val /= max_float
+    return np.around(val * gs.MAX_DN).astype(np.uint8)
+
+
 def _imread(path: str, flags=None):
     import cv2 as cv
     return cv.imread(path) if flags is None else cv.imread(path, flags)
@@ -273,19 +287,12 @@ class ImageSet(object):
         file_path = self.path.parent.joinpath('8bit', self.path.name) if save_path is None else save_path
         file_path.parent.mkdir(parents=True, exist_ok=True)
         file_path = str(file_path)
-        val, std = self.measurand.numpy()
-        val = val.astype(np.float64, copy=True)
-        max_float = np.amax(val)
-        if max_float > 1:
-            val /= max_float
-        cv.imwrite(file_path, np.around(val * gs.MAX_DN).astype(np.uint8))
-        if std is not None:
-            std = std.copy()
+        cv.imwrite(file_path, _quantize_8bit(self.measurand.val))
+        if self.measurand.std is not None:
             if force_8_bit:
-                max_float = np.amax(std)
-                if max_float > 1:
-                    std /= max_float
-                std = np.around(std * gs.MAX_DN).astype(np.uint8)
+                std = _quantize_8bit(self.measurand.std)
+            else:
+                std = self.measurand.numpy()[1]
             cv.imwrite(file_path.removesuffix('.tif') + ' STD.tif', std)
 
     @classmethod

@@ -482,6 +482,25 @@ def pair_statistics(x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor, y_std
     return stats
 
 
+# ------------------------------------------------------------------------------------- egress
+def quantize_8bit(val: Tensor, max_dn: float = 255.0, return_max: bool = False):
+    """The array part of ImageSet.save_8bit (image_set.py:343-350): normalise by ``amax`` when it exceeds 1,
+    scale by MAX_DN, round half-even, cast to uint8 -- on the device, so the result crosses PCIe as one
+    byte per sample.  Returns the uint8 tensor (and the device scalar ``amax`` if asked)."""
+    _require_cuda(val)
+    if val.numel() == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    lib = _lib.load()
+    v = _f64c(val)
+    out = torch.empty(v.shape, dtype=torch.uint8, device=v.device)
+    mx = torch.empty((), dtype=torch.float64, device=v.device)
+    ws_bytes = lib.cl_quantize_8bit_workspace_bytes()
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
+    check(lib.cl_quantize_8bit(_ptr(v), v.numel(), float(max_dn), _ptr(out), _ptr(mx), _ptr(ws), ws_bytes,
+                               _stream()), "cl_quantize_8bit")
+    return (out, mx) if return_max else out
+
+
 # ------------------------------------------------------------------------------------- custom ops
 # Registered for discoverability / composability with torch.library; they call the functions above.
 @torch.library.custom_op("camera_linearity::linearize", mutates_args=(), device_types="cuda")

@@ -1,9 +1,11 @@
 """Mean / standard-error frames of videos (reference: ``modules/video_processing.py:161-274``).
 
-``welford_algorithm`` keeps the reference's signature.  Frames are decoded on the host (OpenCV),
-moved to the GPU in chunks and folded into the running float64 (mean, M2) state with the exact
-sequential Welford recurrence (``ops.welford_update``, bit-identical to NumPy).  When a whole
-stack is already resident on the device, ``welford_stack`` uses the integer fast path (K3).
+``welford_algorithm`` keeps the reference's signature.  Frames are decoded on the host (OpenCV)
+straight into one of two pinned staging buffers; a full buffer is copied to the device on a copy
+stream while the decoder fills the other one, and folded into the running float64 (mean, M2) state
+with the exact sequential Welford recurrence (``ops.welford_update``, bit-identical to NumPy) --
+decode, H2D and the update overlap.  When a whole stack is already resident
+on the device, ``welford_stack`` uses the integer fast path (K3).
 Repair R9: ``if ICRF is not None``; the float64 mean and SEM are returned next to
 the reference's uint8 outputs.
 """
@@ -33,6 +35,59 @@ def welford_stack(frames, ICRF=None):
     return {'mean': mean_u8, 'std': std_u8, 'mean_f64': mean, 'sem': sem, 'count': int(fr.shape[0])}
 
 
+class _ChunkStager:
+    """Two pinned host buffers of CHUNK_FRAMES frames feeding ``ops.welford_update``.
+
+    push() copies a decoded frame into the buffer being filled; a full buffer is sent to the device on
+    the copy stream and consumed on the current stream, both asynchronously, so the decoder keeps
+    running.  A buffer is reused only after the update that read its device copy has finished
+    (``free[i]`` event).  On the CPU device (host-logic tests) the same code runs without streams."""
+
+    def __init__(self, frame_shape, dev, icrf):
+        self.dev, self.icrf = dev, icrf
+        self.cuda = dev.type == "cuda"
+        shape = (CHUNK_FRAMES,) + tuple(frame_shape)
+        self.host = [torch.empty(shape, dtype=torch.uint8, pin_memory=self.cuda) for _ in range(2)]
+        self.host_np = [h.numpy() for h in self.host]
+        self.device = [torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(2)] if self.cuda else self.host
+        self.copy_stream = torch.cuda.Stream(dev) if self.cuda else None
+        self.free = [None, None]
+        self.i = self.fill = self.count = 0
+        self.mean = torch.zeros(tuple(frame_shape), dtype=torch.float64, device=dev)
+        self.m2 = torch.zeros_like(self.mean)
+
+    def push(self, frame):
+        if self.fill == 0 and self.free[self.i] is not None:
+            self.free[self.i].synchronize()                 # the previous user of this buffer pair is done
+        self.host_np[self.i][self.fill] = frame
+        self.fill += 1
+        if self.fill == CHUNK_FRAMES:
+            self._flush()
+
+    def _flush(self):
+        n, i = self.fill, self.i
+        if n == 0:
+            return
+        chunk = self.device[i][:n]
+        if self.cuda:
+            main = torch.cuda.current_stream(self.dev)
+            with torch.cuda.stream(self.copy_stream):
+                chunk.copy_(self.host[i][:n], non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(self.copy_stream)
+            main.wait_event(copied)
+        self.count = ops.welford_update(chunk, self.mean, self.m2, self.count, self.icrf, gs.MAX_DN)
+        if self.cuda:
+            self.free[i] = torch.cuda.Event()
+            self.free[i].record(torch.cuda.current_stream(self.dev))
+        self.i ^= 1
+        self.fill = 0
+
+    def finish(self):
+        self._flush()
+        return self.mean, self.m2, self.count
+
+
 def welford_algorithm(file_paths: Union[Path, List[Path]], ICRF=None, use_std: Optional[bool] = False,
                       frame_source=None):
     """Welford mean / std frame over all frames of one or more videos (video_processing.py:161-219).
@@ -46,31 +101,17 @@ def welford_algorithm(file_paths: Union[Path, List[Path]], ICRF=None, use_std: O
     source = gf.video_frame_generator if frame_source is None else frame_source
     dev = gs.device()
     icrf = None if ICRF is None else torch.as_tensor(ICRF, dtype=torch.float64, device=dev)
-    mean = m2 = None
-    count = 0
-    pending: List[np.ndarray] = []
-
-    def flush():
-        nonlocal mean, m2, count
-        if not pending:
-            return
-        chunk = torch.from_numpy(np.ascontiguousarray(np.stack(pending))).to(dev, non_blocking=True)
-        pending.clear()
-        if mean is None:
-            mean = torch.zeros(chunk.shape[1:], dtype=torch.float64, device=dev)
-            m2 = torch.zeros_like(mean)
-        count = ops.welford_update(chunk, mean, m2, count, icrf, gs.MAX_DN)
-
+    stager = None
     for file_path in file_paths:
         for frame in source(file_path):
             if frame is None:
                 break
-            pending.append(frame)
-            if len(pending) == CHUNK_FRAMES:
-                flush()
-    flush()
-    if mean is None:
+            if stager is None:
+                stager = _ChunkStager(np.asarray(frame).shape, dev, icrf)
+            stager.push(frame)
+    if stager is None:
         raise ValueError("no frames decoded")
+    mean, m2, count = stager.finish()
     sem, mean_u8 = ops.welford_finalize(mean, m2 if use_std else None, count, gs.MAX_DN)
     std_u8 = None
     if use_std:

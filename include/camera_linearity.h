@@ -224,6 +224,18 @@ int cl_pair_statistics(const double* x_val, const double* x_std, const double* y
                        int channels, double* stats /* device [2][3][C] */, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* ---- Egress: 8-bit export ---------------------------------------------------------------------
+ * Replaces the array part of ImageSet.save_8bit (modules/image_set.py:321-358):
+ *   max_float = np.amax(val); if max_float > 1: val /= max_float
+ *   out = np.around(val * max_dn).astype(uint8)
+ * val: n float64 samples (device); out: n bytes (device); out_max: optional device double receiving
+ * np.amax(val) (NaN if any sample is NaN -- then, like the reference, nothing is normalised).
+ * Bytes are identical to NumPy's (IEEE divide / multiply, round-half-even, C cast through int32).
+ * Two launches; workspace holds the per-block maxima. */
+size_t cl_quantize_8bit_workspace_bytes(void);
+int cl_quantize_8bit(const double* val, int64_t n_samples, double max_dn, uint8_t* out, double* out_max,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

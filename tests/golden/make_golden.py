@@ -356,6 +356,32 @@ def golden_linearity(ref):
     np.savez_compressed(OUT / 'k5_linearity.npz', **out)
 
 
+def golden_save_8bit(ref):
+    # ImageSet.save_8bit (image_set.py:321-358), UNMODIFIED, written through OpenCV and read back
+    import tempfile
+    import cv2 as cv
+    NM = ref.measurand.NumpyMeasurand
+    rng = np.random.default_rng(77)
+    out = {}
+    cases = {
+        "hdr": rng.uniform(0, 37.5, (40, 52, 3)),                       # max > 1: normalised
+        "unit": rng.uniform(0, 1, (40, 52, 3)),                         # max <= 1: scaled only
+        "ties": (np.arange(40 * 52 * 3).reshape(40, 52, 3) % 511) / 510.0,   # x.5 ties -> half-even
+        "negative": rng.uniform(-0.4, 2.0, (40, 52, 3)),                # the C cast wraps negatives
+    }
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, val in cases.items():
+            std = rng.uniform(0, 3.0, val.shape)
+            path = Path(tmp) / f"{name} 5ms.tif"
+            iset = ref.image_set.ImageSet(file_path=path, measurand=NM(val.copy(), std.copy()))
+            iset.save_8bit(save_path=Path(tmp) / "out" / path.name, force_8_bit=True)
+            out[f"{name}_val"] = val
+            out[f"{name}_std"] = std
+            out[f"{name}_val_u8"] = cv.imread(str(Path(tmp) / "out" / path.name), -1)
+            out[f"{name}_std_u8"] = cv.imread(str(Path(tmp) / "out" / path.name).removesuffix('.tif') + ' STD.tif', -1)
+    np.savez_compressed(OUT / 'k6_save_8bit.npz', **out)
+
+
 if __name__ == '__main__':
     import warnings
     warnings.simplefilter('ignore')
@@ -364,6 +390,7 @@ if __name__ == '__main__':
     golden_welford(ref)
     golden_energy(ref)
     golden_linearity(ref)
+    golden_save_8bit(ref)
     golden_merge()
     for f in sorted(OUT.glob('*.npz')):
         print(f.name, f.stat().st_size)

@@ -112,3 +112,16 @@ def test_full_size_cfg4_checksum():
     o = ow.welford(list(crop))
     assert np.array_equal(host(mean_u8[500:502, 100:164]), o["mean_u8"])
     np.testing.assert_allclose(host(sem[500:502, 100:164]), o["sem"], rtol=1e-9)
+
+
+def test_welford_algorithm_pinned_double_buffer_many_chunks():
+    # 5 buffer swaps + a ragged last chunk, two "videos": bit-identical to the sequential NumPy recurrence
+    rng = np.random.default_rng(99)
+    a = _video(rng, 3 * 32 + 5, (20, 24, 3))
+    b = _video(rng, 2 * 32 + 17, (20, 24, 3))
+    vids = {"a": a, "b": b}
+    r = cl.welford_algorithm(["a", "b"], None, True, frame_source=lambda p: list(vids[p]) + [None])
+    o = ow.welford(list(a) + list(b))
+    assert r["count"] == len(a) + len(b)
+    assert np.array_equal(host(r["mean_f64"]), o["mean"])
+    assert np.array_equal(host(r["sem"]), o["sem"])

@@ -159,3 +159,15 @@ def test_tiff_roundtrip(tmp_path):
     back.load_value_image(bit64=True)
     back.load_std_image()
     assert np.allclose(back.measurand.val.numpy(), val) and np.allclose(back.measurand.std.numpy(), val * 0.1)
+
+
+def test_save_8bit_files_match_reference(tmp_path, golden_dir):
+    # image_set.py:321-358 through the host shell: the files equal the ones the reference wrote
+    import cv2 as cv
+    g = np.load(golden_dir / "k6_save_8bit.npz")
+    for name in ("hdr", "unit", "ties", "negative"):
+        s = ImageSet(file_path=tmp_path / f"{name} 5ms.tif", value=g[f"{name}_val"], std=g[f"{name}_std"])
+        out = tmp_path / "out" / f"{name} 5ms.tif"
+        s.save_8bit(out, force_8_bit=True)
+        assert np.array_equal(cv.imread(str(out), -1), g[f"{name}_val_u8"])
+        assert np.array_equal(cv.imread(str(out).removesuffix(".tif") + " STD.tif", -1), g[f"{name}_std_u8"])

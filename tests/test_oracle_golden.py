@@ -198,3 +198,12 @@ def test_linearity_chain_matches_reference_bitexact(golden_dir):
                 assert np.array_equal(st["error"], g[f"{tag}_{name}_error"])
             else:
                 assert st["error"] is None
+
+
+# ------------------------------------------------------------------ 8-bit export (8f rank 2)
+def test_save_8bit_matches_reference_bytes(golden_dir):
+    from oracle import egress
+    g = _load(golden_dir, "k6_save_8bit.npz")
+    for name in ("hdr", "unit", "ties", "negative"):
+        assert np.array_equal(egress.quantize_8bit(g[f"{name}_val"]), g[f"{name}_val_u8"])
+        assert np.array_equal(egress.quantize_8bit(g[f"{name}_std"]), g[f"{name}_std_u8"])
