@@ -34,7 +34,7 @@ struct Src<2> {
     using Pair = double2;
 };
 
-constexpr int kSlots = 4;   // pairs of samples per thread; slot u of thread t = pair (u*blockDim + t)
+constexpr int kSlots = 8;   // pairs of samples per thread; slot u of thread t = pair (u*blockDim + t)
 
 template <int SRC>
 __device__ __forceinline__ uint32_t bin_of(typename Src<SRC>::T v, double max_dn, uint32_t wrap_mask) {
@@ -45,7 +45,7 @@ __device__ __forceinline__ uint32_t bin_of(typename Src<SRC>::T v, double max_dn
 // Every warp-level access is contiguous: in slot u the 32 lanes read 32 consecutive sample PAIRS
 // (64 B of uint8, 512 B of float64) and write 512 B -- fully coalesced loads and stores.
 template <int SRC, bool LUT_SMEM>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, SRC == 2 ? 2 : 3)
 linearize_kernel(const typename Src<SRC>::T* __restrict__ src, double max_dn, uint32_t wrap_mask,
                  const double* __restrict__ std_in, const double* __restrict__ lut,
                  const double* __restrict__ dlut, double* __restrict__ out_val,
@@ -70,6 +70,11 @@ linearize_kernel(const typename Src<SRC>::T* __restrict__ src, double max_dn, ui
     const int64_t n_pairs = n / 2;
     const int64_t per_block = (int64_t)kSlots * blockDim.x;
     const int64_t n_blocks_work = (n_pairs + per_block - 1) / per_block;
+    // channel of the first sample of a pair, kept incrementally (a 64-bit modulo per pair cost more
+    // registers and instructions than the rest of the loop): c(q + d) = (c(q) + 2d) mod C
+    const int step_slot = (int)((2 * (int64_t)blockDim.x) % C);
+    const int step_block = (int)((2 * per_block * gridDim.x) % C);
+    int c_first = (int)((2 * ((int64_t)blockIdx.x * per_block + threadIdx.x)) % C);
     for (int64_t b = blockIdx.x; b < n_blocks_work; b += gridDim.x) {
         const int64_t first = b * per_block + threadIdx.x;
         Pair in[kSlots];
@@ -82,14 +87,18 @@ linearize_kernel(const typename Src<SRC>::T* __restrict__ src, double max_dn, ui
                 if (use_std) sd[u] = reinterpret_cast<const double2*>(std_in)[q];
             }
         }
+        int c0 = c_first;
 #pragma unroll
         for (int u = 0; u < kSlots; ++u) {
             const int64_t q = first + (int64_t)u * blockDim.x;
+            const int c_here = c0;
+            c0 += step_slot;
+            if (c0 >= C) c0 -= C;
             if (q < n_pairs) {
                 const uint32_t b0 = bin_of<SRC>(in[u].x, max_dn, wrap_mask);
                 const uint32_t b1 = bin_of<SRC>(in[u].y, max_dn, wrap_mask);
-                const int c0 = (int)((2 * q) % C);
-                const int c1 = (c0 + 1 == C) ? 0 : c0 + 1;
+                const int c0 = c_here;
+                const int c1 = (c0 + 1 >= C) ? c0 + 1 - C : c0 + 1;
                 const int i0 = (int)b0 * C + c0, i1 = (int)b1 * C + c1;
                 reinterpret_cast<double2*>(out_val)[q] = make_double2(tv[i0], tv[i1]);
                 if (use_std)
@@ -98,6 +107,8 @@ linearize_kernel(const typename Src<SRC>::T* __restrict__ src, double max_dn, ui
                 if (bin_out) reinterpret_cast<ushort2*>(bin_out)[q] = make_ushort2((uint16_t)b0, (uint16_t)b1);
             }
         }
+        c_first += step_block;
+        if (c_first >= C) c_first -= C;
     }
     // odd tail sample
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -124,7 +135,7 @@ int launch(const void* src, double max_dn, const double* std_in, const double* l
     const bool lut_smem = lut_bytes <= 96 * 1024;
     const int64_t per_block = (int64_t)kSlots * kThreads;
     int64_t blocks = (n / 2 + per_block - 1) / per_block;
-    const int64_t cap = (int64_t)sm_count() * 8;  // 8 resident CTAs of 256 threads per SM
+    const int64_t cap = (int64_t)sm_count() * (SRC == 2 ? 2 : 3);   // one wave of resident CTAs
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (lut_smem) {

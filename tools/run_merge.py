@@ -1,6 +1,6 @@
 """Run ops.hdr_merge on the cfg2 bench stack a few times (profiling target for ncu).
 
-    python tools/run_merge.py [dark_threshold] [reps]
+    python tools/run_merge.py [dark_threshold] [reps] [darks:0|1] [flat:0|1]
 """
 import sys
 from pathlib import Path
@@ -17,6 +17,8 @@ from camera_linearity_b200 import ops  # noqa: E402
 def main():
     thr = float(sys.argv[1]) if len(sys.argv) > 1 else bench.DARK_THRESHOLD
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    use_darks = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
+    use_flat = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
     dev = torch.device("cuda:0")
     wl = bench.WORKLOADS["cfg2"]
     data = bench.make_stack_device(wl, 1234, dev)
@@ -25,6 +27,10 @@ def main():
     t = [float(x) for x in data["t"]]
     roi = cl.measurand._flat_roi()
     means = ops.flat_roi_means(data["flat"], data["flat_std"], roi)
+    if not use_darks:
+        data["darks"] = None
+    if not use_flat:
+        data["flat"] = data["flat_std"] = means = None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
     ev[0].record()
     for r in range(reps):
@@ -33,7 +39,7 @@ def main():
                             flat_means=means)
         ev[r + 1].record()
     torch.cuda.synchronize()
-    print("threshold", thr, "ms per call:", [round(ev[r].elapsed_time(ev[r + 1]), 4) for r in range(reps)])
+    print("threshold", thr, "darks", use_darks, "flat", use_flat, "ms per call:", [round(ev[r].elapsed_time(ev[r + 1]), 4) for r in range(reps)])
 
 
 if __name__ == "__main__":
