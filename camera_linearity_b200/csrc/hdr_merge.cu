@@ -594,7 +594,7 @@ extern "C" {
 size_t cl_hdr_merge_workspace_bytes(const cl_hdr_merge_args* a) {
     if (!a) return 0;
     size_t bytes = 0;
-    if (a->bits > 256) bytes += cl::table_bytes(a->bits, a->channels);
+    if (a->bits > 256) bytes += cl::table_bytes(a->bits, a->channels);   // (the fused-table kernel needs less)
     // bad-pixel work list of the staged kernel (uint8, 3 channels, dark frames present)
     bool any_dark = false;
     if (a->dark)
@@ -667,6 +667,17 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
 
     cudaStream_t s = (cudaStream_t)stream;
     const bool tab_smem = a->bits <= 256;
+    // 16-bit stacks with uncertainty images and N <= 16: fused-table kernel (hdr_merge_wide.cu)
+    bool wide = false;
+    if (!tab_smem && a->algo != 1 && a->algo != 2) {
+        if (workspace && aligned(workspace, 16) && workspace_bytes >= wide_table_bytes(p.bits, p.C))
+            p.g_tab32 = reinterpret_cast<const double2*>(workspace);
+        wide = merge_wide_supported(p, a->dn_bytes, all_std);
+        if (a->algo == 3 && !wide) return p.g_tab32 ? CL_ERR_UNSUPPORTED : CL_ERR_WORKSPACE;
+    } else if (a->algo == 3) {
+        return CL_ERR_UNSUPPORTED;
+    }
+    if (wide) return launch_merge_wide(p, s);
     if (!tab_smem) {
         const size_t need = table_bytes(p.bits, p.C);
         if (!workspace || workspace_bytes < need) return CL_ERR_WORKSPACE;

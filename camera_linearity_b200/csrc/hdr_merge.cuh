@@ -30,6 +30,8 @@ struct MergeParams {
     // tables in global memory (16-bit path): wt[bits], pb[bits][C] = {w*g, dlut}
     const double* g_wt;
     const double2* g_pb;
+    // interleaved tables of the 16-bit kernel (hdr_merge_wide.cu): [bits][C] x {lut, dlut}
+    const double2* g_tab32;
     // bad-pixel work list of the staged path (see hdr_merge_staged.cu): sample indices whose dark
     // frame exceeds the threshold in at least one exposure; hot_list[0] is the counter
     uint32_t* hot_list;
@@ -204,6 +206,9 @@ __device__ __forceinline__ double flat_recip(const void* flat, int flat_bytes, i
 }
 
 int launch_merge_staged(const MergeParams& p, cudaStream_t stream);   // hdr_merge_staged.cu
+int launch_merge_wide(const MergeParams& p, cudaStream_t stream);     // hdr_merge_wide.cu
+bool merge_wide_supported(const MergeParams& p, int dn_bytes, bool all_std_images);
+size_t wide_table_bytes(int bits, int C);
 bool merge_staged_supported(const MergeParams& p, bool all_std_images);
 // hdr_merge.cu
 int launch_merge_generic_range(const MergeParams& p, int64_t first_item, cudaStream_t stream);

@@ -112,7 +112,8 @@ typedef struct cl_hdr_merge_args {
     double* out_val;              /* device (H,W,C) f64                                     */
     double* out_std;              /* device (H,W,C) f64                                     */
     int32_t algo;                 /* 0 = auto, 1 = generic register kernel,
-                                     2 = bulk-copy staged kernel (uint8, C = 3 or 1)         */
+                                     2 = bulk-copy staged kernel (uint8, C = 3),
+                                     3 = fused-table kernel (uint16, std images, N <= 16)    */
     int32_t reserved;
 } cl_hdr_merge_args;
 

@@ -207,3 +207,15 @@ def test_save_8bit_matches_reference_bytes(golden_dir):
     for name in ("hdr", "unit", "ties", "negative"):
         assert np.array_equal(egress.quantize_8bit(g[f"{name}_val"]), g[f"{name}_val_u8"])
         assert np.array_equal(egress.quantize_8bit(g[f"{name}_std"]), g[f"{name}_std_u8"])
+
+
+def test_reciprocal_quotient_is_exact():
+    # csrc/hdr_merge_wide.cu evaluates dn / MAX_DN as fma(fma(-q0, MAX, dn), RN(1/MAX), q0), q0 = dn * RN(1/MAX);
+    # that equals the IEEE quotient NumPy computes for every 8- and 16-bit dn (exact rational check)
+    from fractions import Fraction as F
+    for b in (255.0, 65535.0):
+        r = 1.0 / b
+        for d in range(int(b) + 1):
+            q0 = d * r
+            rem = float(F(d) - F(q0) * F(b))
+            assert float(F(rem) * F(r) + F(q0)) == d / b
