@@ -196,13 +196,18 @@ energy_partial_kernel(const double2* __restrict__ tables, int D, const uint8_t* 
     }
 }
 
+// One warp per output: lanes stride over the CTAs, then an xor tree -- a fixed order, so the result is
+// deterministic (a single thread walking all CTAs' partials took 13 us of a 150 us evaluation).
 __global__ void reduce_ctas_kernel(const double* __restrict__ cta_partial, int n_ctas, int64_t per_cta,
                                    double* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= per_cta) return;
     double s = 0.0;
-    for (int c = 0; c < n_ctas; ++c) s += cta_partial[(int64_t)c * per_cta + i];
-    out[i] = s;
+#pragma unroll 4
+    for (int c = lane; c < n_ctas; c += 32) s += cta_partial[(int64_t)c * per_cta + i];
+    s = warp_sum(s);
+    if (lane == 0) out[i] = s;
 }
 
 __global__ void finalize_kernel(const double* __restrict__ pair_acc, const int32_t* __restrict__ valid,
@@ -337,8 +342,8 @@ int cl_icrf_energy_partial(const cl_icrf_problem* p, const void* tables, const u
         default: return CL_ERR_UNSUPPORTED;
     }
     if (st != CL_OK) return st;
-    reduce_ctas_kernel<<<(unsigned)((per_cta + 255) / 256), 256, 0, s>>>(cta_partial, pl.chunks, per_cta,
-                                                                        pair_acc);
+    reduce_ctas_kernel<<<(unsigned)((per_cta * 32 + 255) / 256), 256, 0, s>>>(cta_partial, pl.chunks, per_cta,
+                                                                             pair_acc);
     return launched();
 }
 

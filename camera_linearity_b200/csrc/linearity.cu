@@ -167,16 +167,26 @@ pair_pass1_kernel(const PairArgs p, double* __restrict__ partial /* [blocks][kQ1
     block_reduce<kQ1>(acc, C, lanes_used, partial + (int64_t)blockIdx.x * kQ1 * C);
 }
 
-// means[q][c]: q = 0 abs mean, 1 rel mean (+ the pass-1 totals kept for the final kernel)
+// Fixed-order sum of one column of the per-block partials by one warp: lanes stride over the blocks, then
+// an xor tree (deterministic; a single thread walking 444 dependent loads took 40 us).
+__device__ __forceinline__ double column_sum(const double* __restrict__ partial, int n_blocks, int row_len, int col) {
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+#pragma unroll 4
+    for (int b = lane; b < n_blocks; b += 32) s += partial[(int64_t)b * row_len + col];
+    return warp_sum(s);
+}
+
+// means[q][c]: q = 0 abs mean, 1 rel mean (+ the pass-1 totals kept for the final kernel); one warp per total
 __global__ void pair_means_kernel(const double* __restrict__ partial, int n_blocks, int C,
                                   double* __restrict__ totals /* [kQ1][C] */, double* __restrict__ means /* [2][C] */) {
-    const int t = threadIdx.x;
-    if (t < kQ1 * C) {
-        double s = 0.0;
-        for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)b * kQ1 * C + t];
-        totals[t] = s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int o = warp; o < kQ1 * C; o += (int)(blockDim.x >> 5)) {
+        const double s = column_sum(partial, n_blocks, kQ1 * C, o);
+        if (lane == 0) totals[o] = s;
     }
     __syncthreads();
+    const int t = threadIdx.x;
     if (t < 2 * C) {
         const int which = t / C, c = t % C;                  // 0 = abs, 1 = rel
         means[t] = totals[(which * 4 + 1) * C + c] / totals[(which * 4 + 0) * C + c];
@@ -207,15 +217,15 @@ pair_pass2_kernel(const PairArgs p, const double* __restrict__ means, double* __
     block_reduce<kQ2>(acc, C, lanes_used, partial + (int64_t)blockIdx.x * kQ2 * C);
 }
 
-// stats[which][k][c]: which 0 = absolute, 1 = relative; k 0 = mean, 1 = std, 2 = error
+// stats[which][k][c]: which 0 = absolute, 1 = relative; k 0 = mean, 1 = std, 2 = error; one warp per (which, c)
 __global__ void pair_final_kernel(const double* __restrict__ partial2, int n_blocks, int C, int use_std,
                                   const double* __restrict__ totals, const double* __restrict__ means,
                                   double* __restrict__ stats) {
-    const int t = threadIdx.x;
+    const int t = threadIdx.x >> 5;
     if (t >= 2 * C) return;
     const int which = t / C, c = t % C;
-    double s = 0.0;
-    for (int b = 0; b < n_blocks; ++b) s += partial2[(int64_t)b * kQ2 * C + t];
+    const double s = column_sum(partial2, n_blocks, kQ2 * C, t);
+    if ((threadIdx.x & 31) != 0) return;
     const double denom = totals[(which * 4 + 0) * C + c];                     // sum of weights / count
     stats[(which * 3 + 0) * C + c] = means[t];
     stats[(which * 3 + 1) * C + c] = sqrt(s / denom);
@@ -260,12 +270,12 @@ int cl_pair_statistics(const double* x_val, const double* x_std, const double* y
     else pair_pass1_kernel<false><<<kBlocks, kThreads, 0, s>>>(p, partial1);
     int st = launched();
     if (st != CL_OK) return st;
-    pair_means_kernel<<<1, 64, 0, s>>>(partial1, kBlocks, channels, totals, means);
+    pair_means_kernel<<<1, 1024, 0, s>>>(partial1, kBlocks, channels, totals, means);
     if ((st = launched()) != CL_OK) return st;
     if (use_std) pair_pass2_kernel<true><<<kBlocks, kThreads, 0, s>>>(p, means, partial2);
     else pair_pass2_kernel<false><<<kBlocks, kThreads, 0, s>>>(p, means, partial2);
     if ((st = launched()) != CL_OK) return st;
-    pair_final_kernel<<<1, 32, 0, s>>>(partial2, kBlocks, channels, use_std ? 1 : 0, totals, means, stats);
+    pair_final_kernel<<<1, 32 * 2 * CL_MAX_CHANNELS, 0, s>>>(partial2, kBlocks, channels, use_std ? 1 : 0, totals, means, stats);
     return launched();
 }
 
