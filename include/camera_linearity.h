@@ -113,7 +113,7 @@ typedef struct cl_hdr_merge_args {
     double* out_std;              /* device (H,W,C) f64                                     */
     int32_t algo;                 /* 0 = auto, 1 = generic register kernel,
                                      2 = bulk-copy staged kernel (uint8, C = 3),
-                                     3 = fused-table kernel (uint16, std images, N <= 16)    */
+                                     3 = fused-table kernel (uint16, N <= 16)                */
     int32_t reserved;
 } cl_hdr_merge_args;
 
