@@ -551,6 +551,31 @@ def extra_kernels(dev):
         out[f"k4_icrf_energy_{name}"] = {"ms_per_population": ms, "evals/s": 64 / ms * 1e3,
                                          "pair_evals/s": 64 * 400000 * 10 / ms * 1e3,
                                          "shape": "cfg3: S=64, 400k px x 5 exposures (4.0M pixel-pairs per eval)"}
+    # DE generations per second on cfg3 (no std): scipy's host loop around the GPU objective vs the
+    # device-resident generation (cl_de_trial -> K4 -> cl_de_select, no host round trip)
+    import time
+    from scipy.optimize._differentialevolution import DifferentialEvolutionSolver
+    from scipy.stats import qmc
+    ev = cl.EnergyEvaluator(x ** 2.2, pca, stack, None, 5, 250, True, tt, 64, shard=False)
+    gens = 60
+    limits = [[-0.5, 0.5]] * 5
+    with DifferentialEvolutionSolver(lambda pop: ev(np.asarray(pop)), limits, strategy='currenttobest1bin', tol=0.0,
+                                     x0=[0.0] * 5, mutation=(0, 1.95), recombination=0.4, init='sobol', rng=7,
+                                     popsize=12, vectorized=True, updating='deferred', polish=False) as solver:
+        for _ in range(5):
+            next(solver)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(gens):
+            next(solver)
+        torch.cuda.synchronize()
+        host_ms = (time.perf_counter() - t0) / gens * 1e3
+    unit = qmc.Sobol(d=5, seed=np.random.default_rng(7)).random(n=64)
+    de = ops.DeviceDE(ev.device_energies, [-0.5] * 5, [0.5] * 5, torch.from_numpy(unit).to(dev), seed=7, tol=0.0)
+    dev_ms = timed(de.step, reps=gens, warm=5)
+    out["k4_de_generation"] = {"scipy_host_loop_ms": host_ms, "device_resident_ms": dev_ms,
+                               "generations/s_device": 1e3 / dev_ms, "evals/s_device": 64e3 / dev_ms,
+                               "shape": "cfg3 without std, 64 members x 5 parameters"}
     return out
 
 

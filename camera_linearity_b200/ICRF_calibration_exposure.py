@@ -72,6 +72,17 @@ class EnergyEvaluator:
         e = plan.finalize().cpu().numpy()
         return float(e[0]) if single else e
 
+    def device_energies(self, params: torch.Tensor) -> torch.Tensor:
+        """params: (S, n_params) device tensor -> (S,) device tensor; nothing synchronises with the host
+        (the objective of the device-resident DE driver)."""
+        plan = self.plan
+        plan.set_params(params)
+        plan.curves_and_tables()
+        acc = plan.partial()
+        if self.sharded:
+            parallel.allreduce_pair_sums(acc)
+        return plan.finalize()
+
 
 def _energy_function(PCA_params, mean_ICRF, PCA_array, image_value_stack, image_std_stack, lower, upper,
                      use_mean, exposure_values):
@@ -119,10 +130,43 @@ def initialize_channel_image_stacks(image_path: Path, use_std: bool, data_spacin
     return value_stacks, std_stacks, np.array(exposures)
 
 
+def _solve_channel_device(mean_ICRF, PCA_array, image_value_stack, image_std_stack, exposure_values, limits, x0,
+                          data_limits, use_mean_ICRF, seed, energy_limit, max_iterations, popsize, check_every=8):
+    """The same solve with the DE generation on the GPU (``ops.DeviceDE``): trial vectors, the population
+    objective (K4) and the selection are enqueued back to back; the host looks at the status block every
+    ``check_every`` generations.  Initial population as scipy's ``init='sobol'`` (2**ceil(log2(popsize*P))
+    members, ``x0`` in row 0); random draws are counter based, so the search is statistically -- not bitwise --
+    scipy's."""
+    from scipy.stats import qmc
+    limits = np.asarray(limits, dtype=np.float64)
+    lower, upper = limits[:, 0], limits[:, 1]
+    n_params = limits.shape[0]
+    members = int(2 ** np.ceil(np.log2(popsize * n_params)))
+    unit = qmc.Sobol(d=n_params, seed=np.random.default_rng(seed)).random(n=members)
+    arg1, arg2 = 0.5 * (lower + upper), np.fabs(upper - lower)
+    unit[0] = (np.asarray(x0, dtype=np.float64) - arg1) / arg2 + 0.5
+    evaluator = EnergyEvaluator(mean_ICRF, PCA_array, image_value_stack, image_std_stack, data_limits[0],
+                                data_limits[1], use_mean_ICRF, exposure_values, members)
+    de = ops.DeviceDE(evaluator.device_energies, lower, upper, torch.from_numpy(unit).to(gs.device()), seed)
+    iterations = 0
+    energy = float("inf")
+    while iterations < max_iterations:
+        burst = min(check_every, max_iterations - iterations)
+        for _ in range(burst):
+            de.step()
+        converged, iterations, energy = de.poll()
+        if converged or energy < energy_limit:
+            break
+    result = de.x.cpu().numpy()
+    return _inverse_camera_response_function(mean_ICRF, PCA_array, result, use_mean_ICRF), result, energy, iterations
+
+
 def solve_channel(mean_ICRF, PCA_array, image_value_stack, image_std_stack, exposure_values, limits, x0,
                   data_limits=(5, 250), use_mean_ICRF=True, seed=7, energy_limit=0.0, max_iterations=1000,
-                  popsize=12):
+                  popsize=12, driver="scipy"):
     """One channel's differential-evolution solve (ICRF_calibration_exposure.py:341-378).
+
+    ``driver='device'`` keeps the whole generation on the GPU (``_solve_channel_device``).
 
     SciPy's solver runs on the host with the reference's settings (currenttobest1bin, tol 0.01,
     mutation (0, 1.95), recombination 0.4, Sobol init); ``vectorized=True, updating='deferred'``
@@ -130,6 +174,12 @@ def solve_channel(mean_ICRF, PCA_array, image_value_stack, image_std_stack, expo
     ``seed=`` keyword (D15); the stop rule (converged / max_iterations / energy below limit) is the
     reference's, one generation per loop step.
     """
+    if driver == "device":
+        return _solve_channel_device(mean_ICRF, PCA_array, image_value_stack, image_std_stack, exposure_values,
+                                     limits, x0, data_limits, use_mean_ICRF, seed, energy_limit, max_iterations,
+                                     popsize)
+    if driver != "scipy":
+        raise ValueError("driver must be 'scipy' or 'device'")
     from scipy.optimize._differentialevolution import DifferentialEvolutionSolver
     evaluator = None
 
@@ -157,9 +207,10 @@ def solve_channel(mean_ICRF, PCA_array, image_value_stack, image_std_stack, expo
 def calibration(lower_PCA_limit: float, upper_PCA_limit: float, initial_function=None, data_spacing=150,
                 data_limits=(5, 250), use_std: Optional[bool] = False, image_path: Optional[Path] = None,
                 energy_limit: Optional[float] = 0, rng_seed: Optional[int] = 7, use_cupy: Optional[bool] = False,
-                max_iterations: int = 1000):
+                max_iterations: int = 1000, driver: str = "scipy"):
     """Driver with the reference's signature and return tuple (ICRF_calibration_exposure.py:288-402).
-    Channels are solved one after another on the GPU (the reference forks one process per channel)."""
+    Channels are solved one after another on the GPU (the reference forks one process per channel).
+    ``driver='device'`` runs the differential evolution itself on the GPU (see ``solve_channel``)."""
     image_path = gs.DEFAULT_IMG_SRC_PATH if image_path is None else image_path
     use_mean_ICRF = initial_function is None
     limits, x0 = [], []
@@ -178,7 +229,8 @@ def calibration(lower_PCA_limit: float, upper_PCA_limit: float, initial_function
         pca = gf.read_txt_to_array(gs.PCA_FILES[c])
         mean = gf.read_txt_to_array(gs.MEAN_ICRF_FILES[c]) if use_mean_ICRF else initial_function
         curve, _, energy, _ = solve_channel(mean, pca, value_stacks[c], std_stacks[c], exposure_values, limits, x0,
-                                            data_limits, use_mean_ICRF, rng_seed + c, energy_limit, max_iterations)
+                                            data_limits, use_mean_ICRF, rng_seed + c, energy_limit, max_iterations,
+                                            driver=driver)
         ICRF[:, c] = curve
         ICRF[:, c] += 1 - ICRF[-1, c]
         ICRF[0, c] = 0

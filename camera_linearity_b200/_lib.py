@@ -77,6 +77,8 @@ SIGNATURES = {
     "cl_icrf_energy_partial": (_i, [C.POINTER(IcrfProblem), _vp, _vp, _vp, C.POINTER(C.c_double),
                                     _i64, _vp, _vp, _sz, _vp]),
     "cl_icrf_energy_finalize": (_i, [C.POINTER(IcrfProblem), _vp, _vp, _vp, _vp]),
+    "cl_de_trial": (_i, [_vp, _i, _i, _d, _d, _d, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cl_de_select": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp]),
     "cl_quantize_8bit_workspace_bytes": (_sz, []),
     "cl_quantize_8bit": (_i, [_vp, _i64, _d, _vp, _vp, _vp, _sz, _vp]),
     "cl_pair_statistics_workspace_bytes": (_sz, [_i]),

@@ -453,6 +453,57 @@ class IcrfEnergyPlan:
         return self.finalize()
 
 
+class DeviceDE:
+    """Differential evolution with the population on the device (``csrc/de.cu``): scipy's
+    'currenttobest1bin' / dither / deferred-updating generation as two kernels around a caller-supplied
+    population objective ``evaluate(params (S, P) device tensor) -> energies (S,) device tensor``.
+    Nothing in ``step()`` synchronises with the host; ``poll()`` reads the 32-byte status block."""
+
+    def __init__(self, evaluate, lower, upper, init_unit_population: Tensor, seed: int, dither=(0.0, 1.95),
+                 recombination: float = 0.4, tol: float = 0.01, atol: float = 0.0):
+        dev = _require_cuda(init_unit_population)
+        self.lib = _lib.load()
+        self.evaluate = evaluate
+        self.pop = _f64c(init_unit_population).clone()
+        self.S, self.P = (int(v) for v in self.pop.shape)
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.lower = torch.as_tensor(np.asarray(lower, dtype=np.float64)).to(dev)
+        self.upper = torch.as_tensor(np.asarray(upper, dtype=np.float64)).to(dev)
+        self.trial = torch.empty_like(self.pop)
+        self.params = torch.empty_like(self.pop)
+        self.generation = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.best = torch.zeros(3, **f64)
+        self.seed, self.dither, self.cr, self.tol, self.atol = int(seed), dither, float(recombination), float(tol), float(atol)
+        # energies of the initial population (scipy: _calculate_population_energies + _promote_lowest_energy)
+        self.energies = self.evaluate(self.scaled(self.pop)).clone()
+        l = int(torch.argmin(self.energies))
+        if l != 0:
+            self.pop[[0, l]] = self.pop[[l, 0]]
+            self.energies[[0, l]] = self.energies[[l, 0]]
+
+    def scaled(self, unit: Tensor) -> Tensor:
+        return 0.5 * (self.lower + self.upper) + (unit - 0.5) * torch.abs(self.upper - self.lower)
+
+    def step(self) -> None:
+        check(self.lib.cl_de_trial(_ptr(self.pop), self.S, self.P, float(self.dither[0]), float(self.dither[1]), self.cr,
+                                   self.seed, _ptr(self.generation), _ptr(self.lower), _ptr(self.upper),
+                                   _ptr(self.trial), _ptr(self.params), _stream()), "cl_de_trial")
+        trial_energies = self.evaluate(self.params)
+        check(self.lib.cl_de_select(_ptr(self.pop), _ptr(self.energies), _ptr(self.trial), _ptr(trial_energies),
+                                    self.S, self.P, self.tol, self.atol, _ptr(self.generation), _ptr(self.status),
+                                    _ptr(self.best), _stream()), "cl_de_select")
+
+    def poll(self):
+        """(converged, generations, best energy) -- one small device-to-host read."""
+        st = self.status.cpu()
+        return bool(st[0]), int(st[1]), float(self.best[0].cpu())
+
+    @property
+    def x(self) -> Tensor:
+        return self.scaled(self.pop[0])
+
+
 # ------------------------------------------------------------------------------------- linearity
 def pair_statistics(x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor, y_std: Optional[Tensor],
                     multiplier: float, lower: Optional[Sequence[Optional[float]]] = None,

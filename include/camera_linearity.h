@@ -237,6 +237,25 @@ size_t cl_quantize_8bit_workspace_bytes(void);
 int cl_quantize_8bit(const double* val, int64_t n_samples, double max_dn, uint8_t* out, double* out_max,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Differential evolution on the device (calibration driver) -----------------------------------
+ * Replaces the host loop of scipy's DifferentialEvolutionSolver as the reference configures it
+ * (modules/ICRF_calibration_exposure.py:357-361: 'currenttobest1bin', mutation (0, 1.95) = dither,
+ * recombination 0.4, tol 0.01), in its vectorized 'deferred' form.  One generation =
+ *   cl_de_trial -> cl_icrf_curves / cl_icrf_energy_partial / [all-reduce] / cl_icrf_energy_finalize -> cl_de_select
+ * All pointers are device pointers.  pop: [S][P] in the unit cube, row 0 = best member; energies [S];
+ * generation: one int64 counter (read by cl_de_trial, incremented by cl_de_select); lower / upper [P];
+ * trial [S][P] (unit cube) and params [S][P] (scaled, the input of cl_icrf_curves) are outputs.
+ * Random draws are counter based (splitmix64 keyed by seed, generation, member, slot): see oracle/de.py.
+ * status [4] int32 = {converged, generations done, members replaced, previous index of the best};
+ * best [3] = {lowest energy, std(E), mean(E)}.  Converged <=> no +inf energy and
+ * std(E) <= atol + tol * |mean(E)|  (scipy's rule). */
+int cl_de_trial(const double* pop, int n_members, int n_params, double dither_lo, double dither_hi,
+                double crossover, uint64_t seed, const int64_t* generation, const double* lower,
+                const double* upper, double* trial, double* params, void* stream);
+int cl_de_select(double* pop, double* energies, const double* trial, const double* trial_energies,
+                 int n_members, int n_params, double tol, double atol, int64_t* generation, int32_t* status,
+                 double* best, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,3 +171,31 @@ def test_save_8bit_files_match_reference(tmp_path, golden_dir):
         s.save_8bit(out, force_8_bit=True)
         assert np.array_equal(cv.imread(str(out), -1), g[f"{name}_val_u8"])
         assert np.array_equal(cv.imread(str(out).removesuffix(".tif") + " STD.tif", -1), g[f"{name}_std_u8"])
+
+
+def test_de_oracle_step_properties():
+    # oracle/de.py (the spec of csrc/de.cu): distinct members, crossover floor, bounds, promotion
+    from oracle import de as ode
+    rng = np.random.default_rng(0)
+    S, P = 64, 5
+    pop = rng.uniform(0, 1, (S, P))
+    for gen in range(20):
+        i = np.arange(S)
+        r0 = (ode.draw(9, gen, i, ode.SLOT_R0) * (S - 1)).astype(np.int64)
+        r0 += r0 >= i
+        r1 = (ode.draw(9, gen, i, ode.SLOT_R1) * (S - 2)).astype(np.int64)
+        a, b = np.minimum(i, r0), np.maximum(i, r0)
+        r1 += r1 >= a
+        r1 += r1 >= b
+        assert np.all(r0 != i) and np.all(r1 != i) and np.all(r0 != r1)
+        assert r0.min() >= 0 and r0.max() < S and r1.min() >= 0 and r1.max() < S
+        trial, params = ode.trial_population(pop, 9, gen, (0.0, 1.95), 0.4, [-2] * P, [2] * P)
+        assert trial.min() >= 0 and trial.max() <= 1
+        assert np.all((trial != pop).any(axis=1))            # the fill point always takes the mutant
+        assert np.allclose(params, (trial - 0.5) * 4)
+        e = rng.uniform(0, 1, S)
+        te = rng.uniform(0, 1, S)
+        pop, e2, st = ode.select(pop, e, trial, te)
+        assert e2[0] == e2.min() == min(e.min(), te.min())
+    u = ode.draw(1, 2, np.arange(100000), 3)
+    assert 0.49 < u.mean() < 0.51 and u.min() >= 0 and u.max() < 1
