@@ -280,6 +280,7 @@ def run_ours(args, wl):
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     rank, world, local = parallel.init_from_env()
+    numa_bound = parallel.bind_to_gpu_numa_node(local) if world > 1 else False   # pinned e2e buffers stay NUMA-local
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -434,7 +435,8 @@ def run_ours(args, wl):
                 "d2h_bytes_per_step": world * d2h,
                 "ms_per_step": float(tm.item()) / n_e2e, "steps": n_e2e,
                 "api": "ExposureSeries.process_HDR_image from pinned host tensors; steps alternate between two "
-                       "CUDA streams (D2H of step i overlaps H2D of step i+1); wall-clock timed"},
+                       "CUDA streams (D2H of step i overlaps H2D of step i+1); wall-clock timed",
+                "numa_bound": bool(numa_bound)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "extra": extra,

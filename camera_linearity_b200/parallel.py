@@ -47,6 +47,26 @@ def init_from_env(backend: str | None = None) -> Tuple[int, int, int]:
     return rk, ws, local
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> bool:
+    """Pin this process to the CPUs that are local to its GPU (NVML's ideal CPU affinity), so that pinned
+    staging buffers are first-touched on the GPU's NUMA node and host->device copies do not cross sockets.
+    Best effort: returns False (and changes nothing) when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpus = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpus + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return False
+        os.sched_setaffinity(0, allowed)
+        return True
+    except Exception:
+        return False
+
+
 def shard_range(n_units: int, rank_: int | None = None, world: int | None = None) -> Tuple[int, int]:
     """Contiguous, balanced [lo, hi) slice of ``n_units`` independent units for this rank."""
     r = rank() if rank_ is None else rank_
