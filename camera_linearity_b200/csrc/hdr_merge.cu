@@ -599,10 +599,10 @@ size_t cl_hdr_merge_workspace_bytes(const cl_hdr_merge_args* a) {
     bool any_dark = false;
     if (a->dark)
         for (int k = 0; k < a->n_exposures && k < CL_MAX_EXPOSURES; ++k) any_dark |= a->dark[k] != nullptr;
-    if (any_dark && a->dn_bytes == 1 && a->channels == 3 && a->algo != 1)
+    if (any_dark && a->dn_bytes == 1 && (a->channels == 3 || a->channels == 1) && a->algo != 1)
         bytes += (cl::kHotListHeader + cl::hot_list_entries((int64_t)a->height * a->width * a->channels)) *
                      sizeof(uint32_t) +
-                 cl::bucket_bytes((int64_t)a->height * a->width) + 16;
+                 cl::bucket_bytes((int64_t)a->height * a->width * a->channels / 3) + 16;
     return bytes;
 }
 
@@ -692,14 +692,14 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
         p.g_pb = pb;
     }
 
-    if (p.any_dark && a->dn_bytes == 1 && p.C == 3 && a->algo != 1) {
+    if (p.any_dark && a->dn_bytes == 1 && (p.C == 3 || p.C == 1) && a->algo != 1) {
         const size_t off = tab_smem ? 0 : table_bytes(p.bits, p.C);
         const size_t entries = hot_list_entries((int64_t)p.H * p.W * p.C);
         const size_t list_bytes = ((kHotListHeader + entries) * sizeof(uint32_t) + 15) / 16 * 16;
-        const size_t bkt_bytes = (bucket_bytes((int64_t)p.H * p.W) + 15) / 16 * 16;
+        const size_t bkt_bytes = (bucket_bytes((int64_t)p.H * p.W * p.C / 3) + 15) / 16 * 16;
         if (workspace && aligned(workspace, 16) && workspace_bytes >= off + list_bytes + bkt_bytes) {
             // [bucket counts][hot-list header + entries][bucket entries]
-            p.n_full_tiles = (int32_t)(((int64_t)p.H * p.W) / kStagedTilePx);
+            p.n_full_tiles = (int32_t)(((int64_t)p.H * p.W * p.C) / (kStagedTilePx * 3));
             p.bucket_counts = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(workspace) + off);
             p.hot_list = p.bucket_counts + (size_t)p.n_full_tiles * 4;
             p.hot_cap = (uint32_t)entries;

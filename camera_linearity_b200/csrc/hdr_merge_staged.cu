@@ -1,4 +1,8 @@
-// K2 fast path ("algo 2"): bulk-copy staged HDR merge for 8-bit, 3-channel stacks on sm_100a.
+// K2 fast path ("algo 2"): bulk-copy staged HDR merge for 8-bit, 3-channel stacks on sm_100a -- and for
+// 8-bit mono stacks, which run through the same kernel as "virtual RGB": samples are independent, so a
+// (H, W, 1) image is processed as H*W/3 three-sample pixels with the one LUT column in all three table
+// slots; only the bad-pixel median (true neighbourhood geometry) and the flat-field means (one channel)
+// look at the real channel count.
 //
 // One persistent CTA per SM (grid = #SMs), 16 consumer warps + 2 producer warps + median warp + patcher warp:
 //   * producer warp 0 streams the float64 uncertainty images through a ring of shared-memory
@@ -104,9 +108,12 @@ __device__ __forceinline__ bool consumed_nonneg(double a, double b, double c) {
     return (__double2hiint(a) | __double2hiint(b) | __double2hiint(c)) >= 0;
 }
 
-template <int NMAX>
+// MONO: the stack has one channel and is processed as virtual RGB (see the file header); a template
+// parameter so that the RGB instantiation is exactly the code it was before mono support
+template <int NMAX, bool MONO>
 __global__ void __launch_bounds__(kThreads, 1)
 merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L, const int n_tiles) {
+    constexpr int kCt = MONO ? 1 : kC;           // true channel count
     extern __shared__ __align__(128) unsigned char smem[];
     double* lutA = reinterpret_cast<double*>(smem + L.off_lutA);
     double2* lutB = reinterpret_cast<double2*>(smem + L.off_lutB);
@@ -146,7 +153,8 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
 #pragma unroll
         for (int r = 0; r < kLutACopies; ++r) lutA[d * kLutACopies + r] = w;
         for (int c = 0; c < kC; ++c) {
-            const double2 e = make_double2(w * p.lut[d * kC + c], p.dlut[d * kC + c]);
+            const int cs = MONO ? 0 : c;                     // mono: the single LUT column in every slot
+            const double2 e = make_double2(w * p.lut[d * kCt + cs], p.dlut[d * kCt + cs]);
 #pragma unroll
             for (int r = 0; r < kLutBCopies; ++r) lutB[(c * 256 + d) * kLutBCopies + r] = e;
         }
@@ -205,12 +213,16 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
                 if ((uint32_t)lane < n_patch) {
                     const uint32_t meta = bucket_s[4 + 4 * lane];
                     const int pix = (int)(meta & 511u), c = (int)((meta >> 9) & 3u), ke = (int)((meta >> 11) & 31u);
-                    const int64_t px = (int64_t)tile * kTilePx + pix;
-                    const int y = (int)(px / p.W), x = (int)(px - (int64_t)y * p.W);
+                    // true image coordinates of the sample (mono: every sample is a pixel)
+                    // (32-bit arithmetic: this warp's latency gates a_ready, and the staged path has < 2^32 samples)
+                    const uint32_t tpx = (uint32_t)tile * kTilePx + (uint32_t)pix;
+                    const uint32_t px = MONO ? tpx * kC + (uint32_t)c : tpx;
+                    const int ct = MONO ? 0 : c;
+                    const int y = (int)(px / (uint32_t)p.W), x = (int)(px - (uint32_t)y * (uint32_t)p.W);
                     const uint8_t* img = reinterpret_cast<const uint8_t*>(p.dn[ke]);
                     uint32_t d_new;
                     double s_new;
-                    median_pair(img, p.std[ke], p.std_lut, y, x, c, p.H, p.W, kC, p.K, d_new, s_new);
+                    median_pair(img, p.std[ke], p.std_lut, y, x, ct, p.H, p.W, kCt, p.K, d_new, s_new);
                     abuf_dn[ke * kDnChunk + pix * kC + c] = (uint8_t)d_new;
                     *reinterpret_cast<double*>(bucket_s + 4 + 4 * lane + 2) = s_new;
                 }
@@ -335,9 +347,10 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
                     rf1 = flat_recip(p.flat, p.flat_bytes, i0 + 1, p.max_dn);
                     rf2 = flat_recip(p.flat, p.flat_bytes, i0 + 2, p.max_dn);
                 }
-                flat_apply(v0, u0, (as0 * r0) * r0, rf0, f0, p.flat_means[0], p.flat_means[kC + 0]);
-                flat_apply(v1, u1, (as1 * r1) * r1, rf1, f1, p.flat_means[1], p.flat_means[kC + 1]);
-                flat_apply(v2, u2, (as2 * r2) * r2, rf2, f2, p.flat_means[2], p.flat_means[kC + 2]);
+                constexpr int c1 = MONO ? 0 : 1, c2 = MONO ? 0 : 2;           // flat_means = [C means | C std means]
+                flat_apply(v0, u0, (as0 * r0) * r0, rf0, f0, p.flat_means[0], p.flat_means[kCt + 0]);
+                flat_apply(v1, u1, (as1 * r1) * r1, rf1, f1, p.flat_means[c1], p.flat_means[kCt + c1]);
+                flat_apply(v2, u2, (as2 * r2) * r2, rf2, f2, p.flat_means[c2], p.flat_means[kCt + c2]);
                 __syncwarp();
                 if (lane == 0 && consumed(u0, u1, u2)) mbar_arrive(&empty[s]);
                 if (++s == stages) { s = 0; phase ^= 1; }
@@ -371,8 +384,9 @@ bool make_layout(const MergeParams& p, StagedLayout& L) {
 }  // namespace
 
 bool merge_staged_supported(const MergeParams& p, bool all_std_images) {
-    if (p.C != kC || p.bits != 256 || p.max_dn != 255.0 || !all_std_images) return false;
-    if ((int64_t)p.H * p.W < kTilePx || (int64_t)p.H * p.W * kC >= 0xFFFFFFFFll) return false;
+    if ((p.C != kC && p.C != 1) || p.bits != 256 || p.max_dn != 255.0 || !all_std_images) return false;
+    const int64_t n_samples = (int64_t)p.H * p.W * p.C;
+    if (n_samples < kTilePx * kC || n_samples >= 0xFFFFFFFFll) return false;
     if (p.any_dark && (!p.hot_list || p.hot_cap == 0 || !p.bucket_counts || !p.bucket_entries)) return false;
     if (p.flat_bytes && (!aligned(p.flat_std, 16) || !aligned(p.flat, 16))) return false;
     StagedLayout L;
@@ -382,8 +396,8 @@ bool merge_staged_supported(const MergeParams& p, bool all_std_images) {
 int launch_merge_staged(const MergeParams& p, cudaStream_t stream) {
     StagedLayout L;
     if (!make_layout(p, L)) return CL_ERR_UNSUPPORTED;
-    const int64_t n_px = (int64_t)p.H * p.W;
-    const int n_tiles = (int)(n_px / kTilePx);
+    const int64_t n_samples = (int64_t)p.H * p.W * p.C;
+    const int n_tiles = (int)(n_samples / (kTilePx * kC));
     int grid = sm_count();
     if (grid > n_tiles) grid = n_tiles;
     auto launch = [&](auto kernel) -> int {
@@ -398,14 +412,20 @@ int launch_merge_staged(const MergeParams& p, cudaStream_t stream) {
         st = launch_dark_scan(p, stream);
         if (st != CL_OK) return st;
     }
-    if (p.n <= 8) st = launch(merge_staged_kernel<8>);
-    else if (p.n <= 16) st = launch(merge_staged_kernel<16>);
-    else st = launch(merge_staged_kernel<32>);
+    if (p.C == 1) {
+        if (p.n <= 8) st = launch(merge_staged_kernel<8, true>);
+        else if (p.n <= 16) st = launch(merge_staged_kernel<16, true>);
+        else st = launch(merge_staged_kernel<32, true>);
+    } else {
+        if (p.n <= 8) st = launch(merge_staged_kernel<8, false>);
+        else if (p.n <= 16) st = launch(merge_staged_kernel<16, false>);
+        else st = launch(merge_staged_kernel<32, false>);
+    }
     if (st != CL_OK) return st;
     // pixels past the last full tile (< 512) go through the generic kernel; both kernels run
     // identical arithmetic, so the seam is invisible
     const int64_t tail_first_sample = (int64_t)n_tiles * kTilePx * kC;
-    if (tail_first_sample < n_px * kC) {
+    if (tail_first_sample < n_samples) {
         st = launch_merge_generic_range(p, tail_first_sample / 4, stream);
         if (st != CL_OK) return st;
     }
