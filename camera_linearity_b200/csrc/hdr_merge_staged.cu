@@ -138,7 +138,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerWarps + (patched ? 1 : 0));   // + the patcher: it walks every stage
+            mbar_init(&empty[s], kConsumerWarps);
             mbar_init(&ready[s], 1);
         }
         mbar_init(a_full, 1);
@@ -258,22 +258,14 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
                     if (__any_sync(0xffffffffu, hit))
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // before the TMA refill
                     __syncwarp();
-                    // ready: consumers of a dark exposure's chunk may go.  empty: the patcher is past this stage
-                    // -- consumers take the other chunks straight off full[], so without this the producer could
-                    // lap a lagging patcher and alias its phase parity.
-                    if (lane == 0) { mbar_arrive(&ready[s]); mbar_arrive(&empty[s]); }
+                    if (lane == 0) mbar_arrive(&ready[s]);
                     if (++s == stages) { s = 0; phase ^= 1; }
                 }
             }
         }
     } else {
         // ===== consumers: thread tid owns pixel tid of each tile =====
-        // "stage is ready": the patcher's signal only for exposures whose dark frame can flag a pixel;
-        // every other chunk (and the flat-field chunk) is taken straight off the bulk-copy barrier, which
-        // saves the patcher's hand-off latency on most stages
-        uint32_t dark_mask = 0;
-        for (int j = 0; j < p.n_dark; ++j) dark_mask |= 1u << p.dark_k[j];
-        if (!patched) dark_mask = 0;
+        uint64_t* const c_full = patched ? ready : full;          // what "stage is ready" means
         uint64_t* const c_afull = patched ? a_ready : a_full;
         const double* myA = lutA + (lane & (kLutACopies - 1));
         const double2* myB = lutB + (lane & (kLutBCopies - 1));
@@ -311,7 +303,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
 #pragma unroll
             for (int k = 0; k < NMAX; ++k) {
                 if (k < p.n) {
-                    mbar_wait(((dark_mask >> k) & 1u) ? &ready[s] : &full[s], phase);
+                    mbar_wait(&c_full[s], phase);
                     const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
                     const double g0 = sp[0], g1 = sp[1], g2 = sp[2];
                     const uint32_t q = pk[k];
@@ -334,7 +326,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             double u0, u1, u2;
             const int64_t i0 = px * kC;
             if (has_flat) {
-                mbar_wait(&full[s], phase);
+                mbar_wait(&c_full[s], phase);
                 const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
                 const double f0 = sp[0], f1 = sp[1], f2 = sp[2];
                 double rf0, rf1, rf2;

@@ -1,6 +1,8 @@
 """Summarise an .ncu-rep (one kernel) into a small text file for profiles/.
 
-    python tools/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r01_xxx.txt ["note"]
+    python tools/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r01_xxx.txt ["note"] [extra ncu import args ...]
+
+e.g. ``-k regex:dark_scan -c 1`` to pick one kernel out of a multi-kernel report.
 """
 import csv
 import subprocess
@@ -25,7 +27,8 @@ STALLS = "smsp__average_warps_issue_stalled_"
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     note = sys.argv[3] if len(sys.argv) > 3 else ""
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    extra = sys.argv[4:]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", *extra], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     lines = [f"# {rep}", f"# {note}", ""]
@@ -40,7 +43,7 @@ def main():
             if k.startswith(STALLS) and k.endswith("per_issue_active.ratio") and float(d[k] or 0) >= 0.05:
                 lines.append(f"  {k:85s} {d[k]:>18s}")
         lines.append("")
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", *extra], capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     if len(rows) > 2:
         h = rows[1]
