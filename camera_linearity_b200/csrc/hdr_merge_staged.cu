@@ -269,6 +269,11 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
         uint64_t* const c_afull = patched ? a_ready : a_full;
         const double* myA = lutA + (lane & (kLutACopies - 1));
         const double2* myB = lutB + (lane & (kLutBCopies - 1));
+        // bytes tid*3 .. tid*3+2 of a DN chunk live in words a_word, a_word+1 (the second word of the last
+        // pixel lies just past the chunk -- still inside the A buffer / the bucket that follows it -- and
+        // contributes only the masked-off top byte)
+        const int a_word = (tid * kC) >> 2;
+        const uint32_t a_shift = ((tid * kC) & 3) * 8;
         uint32_t ti = 0, phase = 0;
         int s = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
@@ -280,18 +285,20 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
 #pragma unroll
             for (int k = 0; k < NMAX; ++k) {
                 if (k < p.n) {
-                    const uint8_t* a = abuf_dn + k * kDnChunk + tid * kC;
-                    const uint32_t d0 = a[0], d1 = a[1], d2 = a[2];
+                    // the pixel's 3 DN bytes out of two aligned words (2 shared loads instead of 3 byte loads)
+                    const uint32_t* aw = reinterpret_cast<const uint32_t*>(abuf_dn + k * kDnChunk) + a_word;
+                    const uint32_t q = __funnelshift_r(aw[0], aw[1], a_shift) & 0xFFFFFFu;
+                    const uint32_t d0 = q & 0xFF, d1 = (q >> 8) & 0xFF, d2 = q >> 16;
                     S0 += myA[d0 * kLutACopies];
                     S1 += myA[d1 * kLutACopies];
                     S2 += myA[d2 * kLutACopies];
-                    pk[k] = d0 | (d1 << 8) | (d2 << 16);
+                    pk[k] = q;
                 }
             }
             uint32_t pkf = 0;
             if (flat_u8) {
-                const uint8_t* a = abuf_dn + p.n * kDnChunk + tid * kC;
-                pkf = (uint32_t)a[0] | ((uint32_t)a[1] << 8) | ((uint32_t)a[2] << 16);
+                const uint32_t* aw = reinterpret_cast<const uint32_t*>(abuf_dn + p.n * kDnChunk) + a_word;
+                pkf = __funnelshift_r(aw[0], aw[1], a_shift) & 0xFFFFFFu;
             }
             // release the A buffer; consumed(S) ties the release to the arithmetic that used its bytes
             __syncwarp();
