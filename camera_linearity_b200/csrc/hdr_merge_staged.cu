@@ -356,8 +356,8 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             } else {
                 u0 = sqrt(as0) * r0; u1 = sqrt(as1) * r1; u2 = sqrt(as2) * r2;
             }
-            p.out_val[i0 + 0] = v0; p.out_val[i0 + 1] = v1; p.out_val[i0 + 2] = v2;
-            p.out_std[i0 + 0] = u0; p.out_std[i0 + 1] = u1; p.out_std[i0 + 2] = u2;
+            __stcs(p.out_val + i0 + 0, v0); __stcs(p.out_val + i0 + 1, v1); __stcs(p.out_val + i0 + 2, v2);
+            __stcs(p.out_std + i0 + 0, u0); __stcs(p.out_std + i0 + 1, u1); __stcs(p.out_std + i0 + 2, u2);
         }
     }
 }
