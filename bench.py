@@ -427,7 +427,7 @@ def run_ours(args, wl):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(args.workload) if args.algo != 1 else None, "traffic_source":
                      "ncu dram__bytes_read+write summed over the kernels of one cl_hdr_merge call (merge_staged 4.21 GB + "
-                     "dark scan / flat ROI / fix-up 0.18 GB), profiles/r01_traffic.json", "peak_source": peak_src, "kernel": ("cl_hdr_merge = flat ROI + dark_scan + merge_staged_kernel<16> (94% of the time) + merge_fixup"
+                     "dark scan / flat ROI / fix-up 0.18 GB), profiles/r01_traffic.json", "peak_source": peak_src, "kernel": ("cl_hdr_merge = flat ROI + dark_scan + merge_staged_kernel<16> (93% of the time) + merge_fixup"
                                 if args.algo != 1 else "merge_generic_kernel"),
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
         "cpu_baseline": cpu,
