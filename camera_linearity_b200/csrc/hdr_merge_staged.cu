@@ -146,20 +146,27 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
         mbar_init(a_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // replicated tables (see file header)
-    for (int d = tid; d < 256; d += kThreads) {
-        double w, dw;
-        gaussian_weight(__ddiv_rn((double)d, p.max_dn), w, dw);
+    __syncthreads();          // barriers are initialised: the producer warps start streaming right away,
+                              // under the table construction below (only the consumers use the tables)
+    if (warp < kConsumerWarps) {
+        // replicated tables (see file header): the work is spread over all 512 consumer threads
+        for (int it = tid; it < 256 * 4; it += kTilePx) {
+            const int d = it >> 2, part = it & 3;            // part 0: w[d]; parts 1..3: channel part-1
+            double w, dw;
+            gaussian_weight(__ddiv_rn((double)d, p.max_dn), w, dw);
+            if (part == 0) {
 #pragma unroll
-        for (int r = 0; r < kLutACopies; ++r) lutA[d * kLutACopies + r] = w;
-        for (int c = 0; c < kC; ++c) {
-            const int cs = MONO ? 0 : c;                     // mono: the single LUT column in every slot
-            const double2 e = make_double2(w * p.lut[d * kCt + cs], p.dlut[d * kCt + cs]);
+                for (int r = 0; r < kLutACopies; ++r) lutA[d * kLutACopies + r] = w;
+            } else {
+                const int c = part - 1;
+                const int cs = MONO ? 0 : c;                 // mono: the single LUT column in every slot
+                const double2 e = make_double2(w * p.lut[d * kCt + cs], p.dlut[d * kCt + cs]);
 #pragma unroll
-            for (int r = 0; r < kLutBCopies; ++r) lutB[(c * 256 + d) * kLutBCopies + r] = e;
+                for (int r = 0; r < kLutBCopies; ++r) lutB[(c * 256 + d) * kLutBCopies + r] = e;
+            }
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTilePx) : "memory");    // consumers only
     }
-    __syncthreads();
 
     if (warp == kConsumerWarps) {
         // ===== ring producer: std chunks (tile-major, exposure-minor; flat std last) =====
