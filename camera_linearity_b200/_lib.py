@@ -77,6 +77,7 @@ SIGNATURES = {
     "cl_icrf_energy_partial": (_i, [C.POINTER(IcrfProblem), _vp, _vp, _vp, C.POINTER(C.c_double),
                                     _i64, _vp, _vp, _sz, _vp]),
     "cl_icrf_energy_finalize": (_i, [C.POINTER(IcrfProblem), _vp, _vp, _vp, _vp]),
+    "cl_channel_histogram": (_i, [_vp, _vp, _i64, _i, _i, _i, _d, _d, _vp, _vp, _vp]),
     "cl_de_trial": (_i, [_vp, _i, _i, _d, _d, _d, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cl_de_select": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp]),
     "cl_quantize_8bit_workspace_bytes": (_sz, []),

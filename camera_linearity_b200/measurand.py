@@ -263,11 +263,17 @@ class Measurand:
             self.std[mask] = math.nan
 
     def compute_channel_histogram(self, bins: int, included_range=None, channels=None, use_std=False):
-        """measurand.py:430-469.  Small host-side reduction (NumPy) -- presentation path."""
+        """measurand.py:430-469: np.histogram per channel over the finite values, inverse-sigma weighted with
+        ``use_std``.  Device tensors are binned by ``cl_channel_histogram``; host tensors (GlobalSettings
+        DEVICE == 'cpu', the host-logic tests) by NumPy."""
         if channels is None:
             channels = list(range(gs.NUM_OF_CHS))
-        val, std = self.numpy()
         out = {}
+        if self.val.is_cuda:
+            for c in channels:
+                out[c] = ops.channel_histogram(self.val, self.std if use_std else None, c, bins, included_range)
+            return out
+        val, std = self.numpy()
         for c in channels:
             v = val[..., c]
             mask = np.isfinite(v)

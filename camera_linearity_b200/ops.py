@@ -533,6 +533,43 @@ def pair_statistics(x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor, y_std
     return stats
 
 
+# ------------------------------------------------------------------------------------- histogram
+def channel_histogram(val: Tensor, std: Optional[Tensor], channel: int, bins: int, included_range=None):
+    """np.histogram of the finite values of one channel (measurand.py:430-469), weighted by 1/std when
+    ``std`` is given.  Returns ``(hist, bin_edges)`` as NumPy arrays like np.histogram; only the ``bins``
+    results (and, without a range, the two extrema) cross PCIe."""
+    _require_cuda(val, std)
+    lib = _lib.load()
+    v = _f64c(val)
+    s = _f64c(std)
+    c_total = int(v.shape[-1])
+    n_px = v.numel() // c_total
+    if included_range is None:
+        # np.histogram's _get_outer_edges over the samples that survive the masks
+        col = v.reshape(-1, c_total)[:, channel]
+        keep = torch.isfinite(col)
+        if s is not None:
+            keep &= s.reshape(-1, c_total)[:, channel] != 0
+        kept = col[keep]
+        if kept.numel() == 0:
+            first, last = 0.0, 1.0
+        else:
+            first, last = float(kept.min()), float(kept.max())
+    else:
+        first, last = float(included_range[0]), float(included_range[1])
+        if first > last:
+            raise ValueError("max must be larger than min in range parameter.")
+    if first == last:
+        first, last = first - 0.5, last + 0.5
+    edges_np = np.linspace(first, last, bins + 1, endpoint=True, dtype=np.float64)
+    edges = torch.from_numpy(edges_np).to(v.device)
+    hist = torch.empty(bins, dtype=torch.float64, device=v.device)
+    check(lib.cl_channel_histogram(_ptr(v), _ptr(s), n_px, c_total, int(channel), int(bins), first, last, _ptr(edges),
+                                   _ptr(hist), _stream()), "cl_channel_histogram")
+    h = hist.cpu().numpy()
+    return (h if s is not None else h.astype(np.intp)), edges_np
+
+
 # ------------------------------------------------------------------------------------- egress
 def quantize_8bit(val: Tensor, max_dn: float = 255.0, return_max: bool = False):
     """The array part of ImageSet.save_8bit (image_set.py:343-350): normalise by ``amax`` when it exceeds 1,

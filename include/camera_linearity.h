@@ -256,6 +256,17 @@ int cl_de_select(double* pop, double* energies, const double* trial, const doubl
                  int n_members, int n_params, double tol, double atol, int64_t* generation, int32_t* status,
                  double* best, void* stream);
 
+/* ---- Per-channel histogram -------------------------------------------------------------------------
+ * Replaces the array part of compute_channel_histogram (modules/measurand.py:430-469): np.histogram of
+ * the finite values of channel `channel` of an interleaved (n_pixels, channels) float64 array with `bins`
+ * uniform bins on [first_edge, last_edge]; std != NULL: samples with sigma == 0 are dropped and the rest
+ * weigh 1/sigma.  edges: device [bins + 1] = np.linspace(first_edge, last_edge, bins + 1) (NumPy's edge
+ * corrections compare against them).  hist: device [bins] float64 (exact counts when unweighted); it is
+ * cleared by the call. */
+int cl_channel_histogram(const double* val, const double* std, int64_t n_pixels, int channels, int channel,
+                         int bins, double first_edge, double last_edge, const double* edges, double* hist,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -382,6 +382,27 @@ def golden_save_8bit(ref):
     np.savez_compressed(OUT / 'k6_save_8bit.npz', **out)
 
 
+def golden_histogram(ref):
+    # AbstractMeasurand.compute_channel_histogram (measurand.py:430-469), UNMODIFIED
+    NM = ref.measurand.NumpyMeasurand
+    rng = np.random.default_rng(88)
+    val = rng.normal(0.4, 0.2, (61, 47, 3))
+    val[3, 5, 1] = np.nan
+    val[7, 9, 2] = np.inf
+    val[::7, ::5, 0] = 0.25                       # exact bin edges for bins=8 on (0, 1)
+    std = rng.uniform(0.001, 0.02, val.shape)
+    std[10, 10, :] = 0.0
+    m = NM(val.copy(), std.copy())
+    out = dict(val=val, std=std)
+    for tag, bins, rng_, use_std in (("a", 8, (0.0, 1.0), False), ("b", 64, None, False), ("c", 50, (0.1, 0.7), True),
+                                     ("d", 5000, None, True)):
+        h = m.compute_channel_histogram(bins, rng_, None, use_std)
+        for c in range(3):
+            out[f"{tag}_hist_{c}"] = h[c][0]
+            out[f"{tag}_edges_{c}"] = h[c][1]
+    np.savez_compressed(OUT / 'k7_histogram.npz', **out)
+
+
 if __name__ == '__main__':
     import warnings
     warnings.simplefilter('ignore')
@@ -391,6 +412,7 @@ if __name__ == '__main__':
     golden_energy(ref)
     golden_linearity(ref)
     golden_save_8bit(ref)
+    golden_histogram(ref)
     golden_merge()
     for f in sorted(OUT.glob('*.npz')):
         print(f.name, f.stat().st_size)

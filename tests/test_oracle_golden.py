@@ -219,3 +219,14 @@ def test_reciprocal_quotient_is_exact():
             q0 = d * r
             rem = float(F(d) - F(q0) * F(b))
             assert float(F(rem) * F(r) + F(q0)) == d / b
+
+
+# ------------------------------------------------------------------ channel histogram (8f rank 4)
+def test_channel_histogram_matches_reference(golden_dir):
+    from oracle import histogram as oh
+    g = _load(golden_dir, "k7_histogram.npz")
+    for tag, bins, rng_, use_std in (("a", 8, (0.0, 1.0), False), ("b", 64, None, False), ("c", 50, (0.1, 0.7), True),
+                                     ("d", 5000, None, True)):
+        for c in range(3):
+            h, e = oh.channel_histogram(g["val"], g["std"], c, bins, rng_, use_std)
+            assert np.array_equal(h, g[f"{tag}_hist_{c}"]) and np.array_equal(e, g[f"{tag}_edges_{c}"])
