@@ -403,6 +403,27 @@ def golden_histogram(ref):
     np.savez_compressed(OUT / 'k7_histogram.npz', **out)
 
 
+def golden_operators(ref):
+    # AbstractMeasurand operators with first-order propagation (measurand.py:106-279, 658-681), UNMODIFIED
+    NM = ref.measurand.NumpyMeasurand
+    M = ref.measurand.AbstractMeasurand
+    rng = np.random.default_rng(99)
+    shape = (11, 13, 3)
+    a = NM(rng.uniform(0.2, 2.0, shape), rng.uniform(0.001, 0.05, shape))
+    b = NM(rng.uniform(0.5, 3.0, shape), rng.uniform(0.001, 0.05, shape))
+    k = NM(rng.uniform(0.5, 3.0, shape), None)
+    out = dict(a_val=a.val, a_std=a.std, b_val=b.val, b_std=b.std, k_val=k.val)
+    results = {"add": a + b, "sub": a - b, "mul": a * b, "div": a / b, "pow": a ** b, "neg": -a,
+               "add_nostd": a + k, "mul_nostd": a * k, "div_scalar": a / 2.5, "rmul_scalar": 0.75 * a,
+               "pow_scalar": a ** 2.2, "log_e": a.log_e(), "log_10": a.log_10(),
+               "interp": M.interpolate(a, b, 0.01, 0.04, 0.025)}
+    for name, m in results.items():
+        out[f"{name}_val"] = m.val
+        if m.std is not None:
+            out[f"{name}_std"] = m.std
+    np.savez_compressed(OUT / 'k8_operators.npz', **out)
+
+
 if __name__ == '__main__':
     import warnings
     warnings.simplefilter('ignore')
@@ -413,6 +434,7 @@ if __name__ == '__main__':
     golden_linearity(ref)
     golden_save_8bit(ref)
     golden_histogram(ref)
+    golden_operators(ref)
     golden_merge()
     for f in sorted(OUT.glob('*.npz')):
         print(f.name, f.stat().st_size)

@@ -103,3 +103,10 @@ def test_float_images_without_dn_are_requantised():
     series.process_HDR_image(icrf, diff, dark_list=[], flat_list=[])
     ev, es = om.hdr_merge(dn, std, np.array(t), icrf, diff)
     assert_rel(host(series.merged_image_set.measurand.val), ev, 1e-11)
+
+
+def test_operators_on_device_match_the_unmodified_reference(golden_dir):
+    from gpu_util import dev
+    from test_measurand_contract import _operator_results, check_operator_goldens
+    g = np.load(golden_dir / "k8_operators.npz")
+    check_operator_goldens(_operator_results(cl.Measurand, g, dev), g, 1e-13)

@@ -252,3 +252,29 @@ class TestGeneralFunctions:
             m.linearize(np.zeros((256, 3)))
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             m.apply_gaussian_weight()
+
+
+def _operator_results(M, g, to):
+    a = M(to(g["a_val"]), to(g["a_std"]))
+    b = M(to(g["b_val"]), to(g["b_std"]))
+    k = M(to(g["k_val"]), None)
+    return {"add": a + b, "sub": a - b, "mul": a * b, "div": a / b, "pow": a ** b, "neg": -a,
+            "add_nostd": a + k, "mul_nostd": a * k, "div_scalar": a / 2.5, "rmul_scalar": 0.75 * a,
+            "pow_scalar": a ** 2.2, "log_e": a.log_e(), "log_10": a.log_10(),
+            "interp": M.interpolate(a, b, 0.01, 0.04, 0.025)}
+
+
+def check_operator_goldens(results, g, rtol):
+    for name, m in results.items():
+        val, std = m.numpy()
+        np.testing.assert_allclose(val, g[f"{name}_val"], rtol=rtol, atol=0, err_msg=name)
+        if f"{name}_std" in g.files:
+            np.testing.assert_allclose(std, g[f"{name}_std"], rtol=rtol, atol=0, err_msg=name)
+        else:
+            assert std is None, name
+
+
+def test_operators_match_the_unmodified_reference(golden_dir):
+    # measurand.py:106-279, 658-681 run unmodified by tests/golden/make_golden.py (k8_operators.npz)
+    g = np.load(golden_dir / "k8_operators.npz")
+    check_operator_goldens(_operator_results(Measurand, g, lambda x: x), g, 1e-13)
