@@ -7,7 +7,8 @@
 // (DN bytes only), pass B re-reads the DNs (L1/L2 hits) together with the float64 std stream and
 // accumulates value and variance in float64 registers.  Weight / ICRF tables are pre-multiplied
 // ({w}, {w*g, dICRF}) and live in shared memory for 8-bit data, in an L2-resident workspace for
-// 16-bit data.  The fast path for 8-bit RGB/mono stacks is hdr_merge_staged.cu ("algo 2").
+// 16-bit data.  The fast path for 8-bit RGB/mono stacks is hdr_merge_staged.cu ("algo 2"), the one for
+// 16-bit stacks hdr_merge_wide.cu ("algo 3").
 #include "hdr_merge.cuh"
 
 #include <cstring>

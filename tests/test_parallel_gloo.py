@@ -120,3 +120,12 @@ def test_shard_helpers():
     assert (lo, hi) == (810, 1080) and (src_lo, src_hi) == (809, 1081)
     assert parallel.shard_rows(2160, halo=2, rank_=0, world=8)[2] == 0
     assert parallel.world_size() == 1 and parallel.rank() == 0
+
+
+def test_numa_binding_is_best_effort_without_a_gpu():
+    # no NVML device here: the helper must change nothing and say so
+    import os
+    from camera_linearity_b200 import parallel
+    before = os.sched_getaffinity(0)
+    assert parallel.bind_to_gpu_numa_node(0) in (False, True)
+    assert os.sched_getaffinity(0) <= before and len(os.sched_getaffinity(0)) >= 1
