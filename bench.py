@@ -529,6 +529,8 @@ def extra_kernels(dev):
     nb = frames.numel() + frames[0].numel() * 17
     out["k3_welford_stack"] = {"ms": ms, "GB/s": nb / ms / 1e6, "Gpix*frames/s": 600 * 1080 * 1920 / ms / 1e6,
                                "shape": "cfg4: 600x1080x1920x3 u8"}
+    ms = timed(lambda: ops.welford_stack(frames, icrf, 255.0, ws), reps=3, warm=1)       # linearised frames (ICRF given)
+    out["k3_welford_stack_icrf"] = {"ms": ms, "GB/s": nb / ms / 1e6, "shape": "cfg4 with ICRF[frame, c] as the sample value"}
     del frames, ws
     # K4: cfg3, S=64 candidates, 400k px x 5 exposures
     x = np.linspace(0, 1, 256)
