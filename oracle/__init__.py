@@ -12,12 +12,13 @@ CUDA library is missing (``camera_linearity_b200/_lib.py``).
 
 Parity status of this oracle (see DESIGN.md section 3 and ``tests/test_oracle_golden.py``):
 
-* K4 (calibration loss), K3 (Welford, ICRF=None), single-channel K1, the Gaussian weight and the
-  Measurand operators are pinned against the UNMODIFIED reference functions run in the build
+* K4 (calibration loss), K3 (Welford, with and without an ICRF -- the ICRF branch is reached with an
+  always-true ndarray subclass), single-channel K1, the Gaussian weight, the linearity chain, save_8bit,
+  the channel histogram and the Measurand operators are pinned against the UNMODIFIED reference functions run in the build
   container (``tests/golden/make_golden.py`` imports them from ``/root/reference`` and the
   outputs are committed under ``tests/golden/``), plus the survey's known-answer values.
-* K2 (HDR merge), multi-channel K1, bad-pixel filter, flat-field normalisation and Welford with
-  an ICRF do not run at reference HEAD (defects D1..D13).  For those the golden vectors are
+* K2 (HDR merge), multi-channel K1, bad-pixel filter and flat-field normalisation do not run at
+  reference HEAD (defects D1..D12).  For those the golden vectors are
   produced by driving the reference's own working pieces (``apply_gaussian_weight``,
   ``_linearize_single``, ``scipy.ndimage.median_filter``) through the literal formulae of
   ``exposure_series.py:388-394`` / ``measurand.py:586-602`` with repairs R1..R9 -- i.e. the

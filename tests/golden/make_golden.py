@@ -272,7 +272,9 @@ def golden_welford(ref):
             yield None
         vp.gf.video_frame_generator = gen
         vp.cv.VideoCapture = lambda p: _Cap(frames[0].shape)
-        return vp.welford_algorithm(Path('/tmp/x.avi'), None, True)
+        return vp.welford_algorithm(Path('/tmp/x.avi'), icrf_arg, True)
+
+    icrf_arg = None
 
     hh, ww, cc = np.meshgrid(np.arange(6), np.arange(8), np.arange(3), indexing='ij')
     katw = [((31 * hh + 17 * ww + 5 * cc + 3 * f * f + f * hh) % 256).astype(np.uint8)
@@ -286,6 +288,21 @@ def golden_welford(ref):
     np.savez_compressed(OUT / 'k3_welford.npz', katw=np.stack(katw), katw_mean_u8=r1['mean'],
                         katw_std_u8=r1['std'], frames=np.stack(fr), mean_u8=r2['mean'],
                         std_u8=r2['std'])
+
+    # The ICRF branch (`if ICRF:`, video_processing.py:200) raises for a plain ndarray (defect D13).  An
+    # ndarray SUBCLASS whose truth value is True makes the UNMODIFIED function take that branch: the
+    # linearised-frame Welford is pinned by the reference's own code, not only by the oracle.
+    class TruthyArray(np.ndarray):
+        def __bool__(self):
+            return True
+
+    icrf, _ = icrf_tables(3, base=2.0, step=0.15)
+    icrf_arg = icrf.view(TruthyArray)
+    fr3 = [np.clip(base + rng.integers(-3, 4, base.shape), 0, 255).astype(np.uint8) for _ in range(15)]
+    r3 = run(fr3)
+    r4 = run(katw)
+    np.savez_compressed(OUT / 'k3_welford_icrf.npz', icrf=icrf, frames=np.stack(fr3), mean_u8=r3['mean'],
+                        std_u8=r3['std'], katw_mean_u8=r4['mean'], katw_std_u8=r4['std'])
 
 
 # ----------------------------------------------------------------------------- K4

@@ -125,3 +125,13 @@ def test_welford_algorithm_pinned_double_buffer_many_chunks():
     assert r["count"] == len(a) + len(b)
     assert np.array_equal(host(r["mean_f64"]), o["mean"])
     assert np.array_equal(host(r["sem"]), o["sem"])
+
+
+def test_icrf_variant_matches_the_unmodified_reference(golden_dir):
+    # golden from the reference's own `if ICRF:` branch (always-true ndarray subclass, make_golden.py)
+    g = np.load(golden_dir / "k3_welford_icrf.npz")
+    r = cl.welford_stack(g["frames"], g["icrf"])
+    assert np.array_equal(host(r["mean"]), g["mean_u8"])
+    r2 = cl.welford_algorithm("mem", g["icrf"], True, frame_source=lambda p: list(g["frames"]) + [None])
+    assert np.array_equal(host(r2["mean"]), g["mean_u8"])
+    assert np.array_equal(host(r2["std"]), g["std_u8"])

@@ -230,3 +230,15 @@ def test_channel_histogram_matches_reference(golden_dir):
         for c in range(3):
             h, e = oh.channel_histogram(g["val"], g["std"], c, bins, rng_, use_std)
             assert np.array_equal(h, g[f"{tag}_hist_{c}"]) and np.array_equal(e, g[f"{tag}_edges_{c}"])
+
+
+def test_welford_with_icrf_matches_the_unmodified_reference(golden_dir):
+    # the reference's `if ICRF:` branch, reached with an always-true ndarray subclass (make_golden.py)
+    g = _load(golden_dir, "k3_welford_icrf.npz")
+    from oracle import welford as ow
+    r = ow.welford(list(g["frames"]), g["icrf"])
+    assert np.array_equal(r["mean_u8"], g["mean_u8"]) and np.array_equal(r["std_u8"], g["std_u8"])
+    hh, ww, cc = np.meshgrid(np.arange(6), np.arange(8), np.arange(3), indexing="ij")
+    katw = [((31 * hh + 17 * ww + 5 * cc + 3 * f * f + f * hh) % 256).astype(np.uint8) for f in range(7)]
+    r = ow.welford(katw, g["icrf"])
+    assert np.array_equal(r["mean_u8"], g["katw_mean_u8"]) and np.array_equal(r["std_u8"], g["katw_std_u8"])
