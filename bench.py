@@ -218,17 +218,20 @@ class ClockSampler:
 
     def _loop(self):
         nv = self.nv
+        it = 0
         while self.running:
             try:
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
                 mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 for bit, name in self.REASONS.items():
                     if mask & bit:
                         self.reasons.add(name)
+                if it % 4 == 0:                      # the power query is the slow one
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
             except Exception:
                 pass
-            time.sleep(0.004)
+            it += 1
+            time.sleep(0.001)
 
     def start(self):
         if self.handle is None:
