@@ -24,17 +24,10 @@ from .settings import GlobalSettings as gs
 
 
 def _quantize_8bit(x) -> np.ndarray:
-    """image_set.py:343-350: max-normalise (only when amax > 1), scale by MAX_DN, round half-even, uint8.
-    Device tensors are quantised by the CUDA kernel and cross PCIe as bytes; host arrays (GlobalSettings
-    DEVICE == 'cpu', used by the host-logic tests) follow the same formula in NumPy."""
-    if isinstance(x, torch.Tensor) and x.is_cuda:
-        from . import ops
-        return ops.quantize_8bit(x, gs.MAX_DN).cpu().numpy()
-    val = np.array(x.cpu().numpy() if isinstance(x, torch.Tensor) else x, dtype=np.float64, copy=True)
-    max_float = np.amax(val)
-    if max_float > 1:
-        val /= max_float
-    return np.around(val * gs.MAX_DN).astype(np.uint8)
+    """image_set.py:343-350: max-normalise (only when amax > 1), scale by MAX_DN, round half-even, uint8 --
+    by the CUDA kernel; the bytes cross PCIe, not the float64 image.  No CPU fallback: host tensors raise."""
+    from . import ops
+    return ops.quantize_8bit(torch.as_tensor(x), gs.MAX_DN).cpu().numpy()
 
 
 def _imread(path: str, flags=None):

@@ -264,26 +264,11 @@ class Measurand:
 
     def compute_channel_histogram(self, bins: int, included_range=None, channels=None, use_std=False):
         """measurand.py:430-469: np.histogram per channel over the finite values, inverse-sigma weighted with
-        ``use_std``.  Device tensors are binned by ``cl_channel_histogram``; host tensors (GlobalSettings
-        DEVICE == 'cpu', the host-logic tests) by NumPy."""
+        ``use_std``, binned on the device by ``cl_channel_histogram`` (no CPU fallback: host tensors raise)."""
         if channels is None:
             channels = list(range(gs.NUM_OF_CHS))
-        out = {}
-        if self.val.is_cuda:
-            for c in channels:
-                out[c] = ops.channel_histogram(self.val, self.std if use_std else None, c, bins, included_range)
-            return out
-        val, std = self.numpy()
-        for c in channels:
-            v = val[..., c]
-            mask = np.isfinite(v)
-            weights = None
-            if use_std:
-                s = std[..., c]
-                mask = np.logical_and(mask, s != 0)
-                weights = 1 / s[mask]
-            out[c] = np.histogram(v[mask], bins=bins, range=included_range, weights=weights)
-        return out
+        return {c: ops.channel_histogram(self.val, self.std if use_std else None, c, bins, included_range)
+                for c in channels}
 
     # ---- hot path: sm_100a kernels through the C ABI ----
     def linearize(self, ICRF, ICRF_diff=None):

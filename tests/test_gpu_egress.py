@@ -59,3 +59,25 @@ def test_image_set_save_8bit_from_device(tmp_path, golden_dir):
     s.save_8bit(out, force_8_bit=True)
     assert np.array_equal(cv.imread(str(out), -1), g["hdr_val_u8"])
     assert np.array_equal(cv.imread(str(out).removesuffix(".tif") + " STD.tif", -1), g["hdr_std_u8"])
+
+
+def test_tiff_roundtrip_8bit(tmp_path):
+    # tests/integration/test_integration_image_set.py:48-83, 8-bit half
+    rng = np.random.default_rng(1)
+    val = rng.random((8, 9, 3))
+    s = cl.ImageSet(file_path=tmp_path / "5ms BF a 10x.tif", value=dev(val), std=dev(val * 0.1))
+    s.save_8bit(tmp_path / "8" / "5ms BF a 10x.tif")
+    back = cl.ImageSet(file_path=tmp_path / "8" / "5ms BF a 10x.tif")
+    back.load_value_image()
+    assert np.allclose(host(back.measurand.val), val, atol=0.5 / 255 + 1e-12)
+
+
+def test_save_8bit_all_golden_cases_through_image_set(tmp_path, golden_dir):
+    import cv2 as cv
+    g = np.load(golden_dir / "k6_save_8bit.npz")
+    for name in ("hdr", "unit", "ties", "negative"):
+        s = cl.ImageSet(file_path=tmp_path / f"{name} 5ms.tif", value=dev(g[f"{name}_val"]), std=dev(g[f"{name}_std"]))
+        out = tmp_path / "out" / f"{name} 5ms.tif"
+        s.save_8bit(out, force_8_bit=True)
+        assert np.array_equal(cv.imread(str(out), -1), g[f"{name}_val_u8"])
+        assert np.array_equal(cv.imread(str(out).removesuffix(".tif") + " STD.tif", -1), g[f"{name}_std_u8"])
