@@ -77,6 +77,13 @@ class ImageSet(object):
     def use_cupy(self, _):
         raise AttributeError("use_cupy is a read-only attribute, managing the state of the used array backend.")
 
+    def to_numpy(self):
+        """image_set.py:88-93.  One backend: kept for call compatibility, changes nothing (``measurand.numpy()``
+        returns host copies)."""
+
+    def to_cupy(self):
+        """image_set.py:95-100.  One backend (torch on the device): kept for call compatibility."""
+
     @property
     def dn(self):
         """Integer digital numbers on the device, or None if only float data is held."""
