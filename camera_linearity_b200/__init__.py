@@ -7,7 +7,7 @@ behind a C ABI (``include/camera_linearity.h``), driven through the reference's 
 """
 from .settings import GlobalSettings
 from .measurand import Measurand as _MeasurandClass
-from .measurand import AbstractMeasurand, NumpyMeasurand, MeasurandFactory
+from .measurand import AbstractMeasurand, NumpyMeasurand, MeasurandFactory, measurand_to_numpy, measurand_to_cupy
 from .image_set import ImageSet
 from .exposure_series import ExposureSeries, ExposurePair
 from . import general_functions, ops, parallel, video_processing, ICRF_calibration_exposure
@@ -17,6 +17,6 @@ from .ICRF_calibration_exposure import _energy_function, EnergyEvaluator, calibr
 # `Measurand(val, std, use_cupy=...)` is both the reference's factory call and the class
 Measurand = _MeasurandClass
 
-__all__ = ["GlobalSettings", "Measurand", "AbstractMeasurand", "NumpyMeasurand", "MeasurandFactory",
+__all__ = ["GlobalSettings", "Measurand", "AbstractMeasurand", "NumpyMeasurand", "MeasurandFactory", "measurand_to_numpy", "measurand_to_cupy",
            "ImageSet", "ExposureSeries", "ExposurePair", "welford_algorithm", "welford_stack",
            "_energy_function", "EnergyEvaluator", "calibration", "ops", "parallel"]

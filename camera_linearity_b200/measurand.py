@@ -345,3 +345,13 @@ def MeasurandFactory(val=None, std=None, use_cupy=True):
     """``Measurand(val, std, use_cupy=...)`` factory of measurand_factory.py:10-14; the flag is
     accepted and ignored (single backend)."""
     return Measurand(val, std)
+
+
+def measurand_to_numpy(measurand):
+    """measurand_factory.py:38-56.  One backend: returns the measurand unchanged (``.numpy()`` gives host arrays)."""
+    return measurand
+
+
+def measurand_to_cupy(measurand):
+    """measurand_factory.py:17-35.  One backend (torch tensors on the device): returns the measurand unchanged."""
+    return measurand
