@@ -80,7 +80,7 @@ __global__ void de_select_kernel(double* __restrict__ pop, double* __restrict__ 
     __syncthreads();
     for (int i = threadIdx.x; i < S; i += blockDim.x) {
         const double te = trial_energies[i];
-        if (te < energies[i]) {                            // NaN never replaces
+        if (te <= energies[i]) {                           // scipy _accept_trial: '<=' (a plateau keeps moving); NaN never replaces
             energies[i] = te;
             for (int j = 0; j < P; ++j) pop[i * P + j] = trial[i * P + j];
             atomicAdd(&n_replaced, 1);

@@ -561,14 +561,10 @@ int launch_dark_scan(const MergeParams& p, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(p.bucket_counts, 0,
                                     ((size_t)p.n_full_tiles * 4 + kHotListHeader) * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return cuda_status(e);
-    static int per_sm = 0;               // resident blocks per SM: the grid is exactly one wave
-    if (per_sm == 0) {
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dark_scan_kernel, kScanThreads, 0) != cudaSuccess ||
-            occ < 1)
-            occ = 4;
-        per_sm = occ;
-    }
+    int per_sm = 0;                      // resident blocks per SM: the grid is exactly one wave
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dark_scan_kernel, kScanThreads, 0) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 4;
     dark_scan_kernel<<<sm_count() * per_sm, kScanThreads, 0, stream>>>(p);
     return launched();
 }

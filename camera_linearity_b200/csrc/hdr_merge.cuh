@@ -199,9 +199,10 @@ __device__ __forceinline__ double flat_value(const void* flat, int flat_bytes, i
     return __ddiv_rn((double)reinterpret_cast<const uint8_t*>(flat)[i], max_dn);
 }
 
-// reciprocal of the flat value of sample i
+// reciprocal of the flat value of sample i (the compile-time table is 1/(d/255): only for max_dn == 255, so
+// that a uint8 flat next to a 16-bit stack is scaled by the same max_dn as flat_value / the ROI means)
 __device__ __forceinline__ double flat_recip(const void* flat, int flat_bytes, int64_t i, double max_dn) {
-    if (flat_bytes == 1) return kRecip255.v[reinterpret_cast<const uint8_t*>(flat)[i]];
+    if (flat_bytes == 1 && max_dn == 255.0) return kRecip255.v[reinterpret_cast<const uint8_t*>(flat)[i]];
     return 1.0 / flat_value(flat, flat_bytes, i, max_dn);
 }
 

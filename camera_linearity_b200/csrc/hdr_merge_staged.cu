@@ -101,11 +101,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // compares false), but the compiler cannot prove it, so the mbarrier arrive is ordered after the
 // arithmetic that consumed the loads and the scoreboard guarantees they have returned.
 __device__ __forceinline__ bool consumed(double a, double b, double c) { return !((a + b) + c < 0.0); }
-// Same idea on the integer pipe for the per-exposure release (the FP64 pipe is the busier one):
-// the variance accumulators are sums of squares, so their sign bits are clear -- also for NaN,
-// because CUDA arithmetic returns the canonical (positive) quiet NaN.
+// Same idea on the integer pipe for the per-exposure release (the FP64 pipe is the busier one): the
+// variance accumulators are sums of squares, i.e. >= +0 -- or NaN of EITHER sign (FP64 arithmetic passes
+// an input NaN's sign and payload through, and x86 / NumPy's 0/0 is the negative quiet NaN, so an
+// uncertainty image can hold one).  With m = OR of the three high words the test "m < 0x80000000 or
+// m >= 0xFFF00000" is true for every such value (a set sign bit can only come from a NaN, whose high word is
+// >= 0xFFF00000, and OR-ing more bits in keeps it there) and false only for negative finite numbers, which
+// cannot occur: always true, never provable, NaN safe.
 __device__ __forceinline__ bool consumed_nonneg(double a, double b, double c) {
-    return (__double2hiint(a) | __double2hiint(b) | __double2hiint(c)) >= 0;
+    const uint32_t m = (uint32_t)(__double2hiint(a) | __double2hiint(b) | __double2hiint(c));
+    return m + 0x00100000u < 0x80100000u;
 }
 
 // MONO: the stack has one channel and is processed as virtual RGB (see the file header); a template

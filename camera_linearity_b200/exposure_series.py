@@ -172,8 +172,10 @@ class ExposureSeries(object):
         for image_set in sets:
             if image_set.dn is None and image_set.measurand.val is None:
                 image_set.load_value_image()
-            if image_set.measurand.std is None:
-                image_set.load_std_image(STD_data)
+            if image_set.measurand.std is None and image_set.std_file_exists():
+                image_set.load_std_image(STD_data)          # a '... STD.tif' next to the image wins (image_set.py:228-243)
+            # otherwise the uncertainty is STD_data[DN, c] (image_set.py:365-385): the merge kernel gathers it
+            # from the table itself, so no float64 uncertainty image is built, uploaded or streamed
             d = image_set.digital_numbers()
             dn.append(d)
             std.append(image_set.measurand.std)
@@ -191,7 +193,10 @@ class ExposureSeries(object):
         dev = dn[0].device
         if any(s is None for s in std):
             if STD_data is None:
-                raise ValueError("an exposure has no uncertainty image and no STD_data table was given")
+                try:
+                    STD_data = gf.read_txt_to_array(gs.STD_FILE_NAME)      # image_set.py:377
+                except (FileNotFoundError, OSError, TypeError):
+                    raise ValueError("an exposure has no uncertainty image and no STD_data table was given") from None
             std_lut = torch.as_tensor(STD_data, dtype=torch.float64, device=dev)
 
         reference_set = sets[0]

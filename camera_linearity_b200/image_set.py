@@ -40,14 +40,15 @@ class ImageSet(object):
     def __init__(self, file_path=None, value=None, std=None, features: Optional[Dict] = None,
                  measurand: Optional[Measurand] = None, use_cupy: Optional[bool] = False):
         self.path = Path(file_path) if isinstance(file_path, str) else file_path
-        self._dn = None
+        self._dn_cache = None
+        self._dn_val = None            # (measurand.val tensor derived from the DNs, its version) or None
         if measurand is not None:
             self._measurand = measurand
         else:
             self._measurand = Measurand(value, std)
             v = self._measurand.val
             if v is not None and not v.dtype.is_floating_point:
-                self._dn = v
+                self._set_dn(v, v)
         self._use_cupy = True          # single (GPU) backend; kept as a read-only attribute
         if features is not None:
             self.features = features
@@ -67,7 +68,8 @@ class ImageSet(object):
         if not isinstance(new_measurand, Measurand):
             raise ValueError(f'Expected type {Measurand.backend}, got {type(new_measurand)} instead.')
         self._measurand = new_measurand
-        self._dn = None
+        self._dn_cache = None
+        self._dn_val = None
 
     @property
     def use_cupy(self):
@@ -84,9 +86,33 @@ class ImageSet(object):
     def to_cupy(self):
         """image_set.py:95-100.  One backend (torch on the device): kept for call compatibility."""
 
+    # The decoded integers are a cache of ``measurand.val``: they stay valid only while ``measurand.val`` is
+    # still the very tensor that was derived from them (same object, not written to since).  Assigning
+    # ``measurand.val`` (also to None, the reference's way of releasing an image) or mutating it in place
+    # (``apply_thresholds``) drops them, so ``linearize`` / ``digital_numbers`` always follow the CURRENT value
+    # image as the reference does (measurand.py:502-505).
+    def _set_dn(self, dn, derived_val):
+        self._dn_cache = dn
+        self._dn_val = None if derived_val is None else (derived_val, derived_val._version)
+
+    @property
+    def _dn(self):
+        if self._dn_cache is None:
+            return None
+        current = self._measurand.val
+        if self._dn_val is None:
+            ok = current is None
+        else:
+            ok = current is self._dn_val[0] and current._version == self._dn_val[1]
+        if not ok:
+            self._dn_cache = None
+            self._dn_val = None
+        return self._dn_cache
+
     @property
     def dn(self):
-        """Integer digital numbers on the device, or None if only float data is held."""
+        """Integer digital numbers on the device, or None if only float data is held (or the value image
+        has been replaced / modified since it was decoded)."""
         return self._dn
 
     def digital_numbers(self):
@@ -220,23 +246,33 @@ class ImageSet(object):
     def set_digital_numbers(self, image):
         """Attach an in-memory integer image (what ``cv.imread`` would have returned)."""
         t = torch.as_tensor(np.ascontiguousarray(image) if isinstance(image, np.ndarray) else image)
-        self._dn = t.to(gs.device())
+        if t.dtype.is_floating_point:
+            raise TypeError("digital numbers must be an integer image (uint8 / uint16)")
+        self._measurand.val = None
+        self._set_dn(t.to(gs.device(), non_blocking=True), None)
 
     def load_value_image(self, bit64: Optional[bool] = False):
-        if self._dn is None:
+        dn = self._dn
+        if dn is None:
             if self.path is None:
                 raise ValueError("ImageSet has neither a file path nor in-memory digital numbers")
             img = _imread(str(self.path)) if not bit64 else _imread(str(self.path), -1)
             if img is None:
                 raise FileNotFoundError(str(self.path))
-            self._dn = torch.from_numpy(np.ascontiguousarray(img)).to(gs.device())
-        dn = self._dn
+            dn = torch.from_numpy(np.ascontiguousarray(img)).to(gs.device())
         if not bit64 and not dn.dtype.is_floating_point:
             self._measurand.val = dn.to(torch.float64) / gs.MAX_DN        # image_set.py:223
         else:
             self._measurand.val = dn                                       # :225
         if dn.dtype.is_floating_point:
-            self._dn = None
+            self._dn_cache = None
+            self._dn_val = None
+        else:
+            self._set_dn(dn, self._measurand.val)
+
+    def std_file_exists(self) -> bool:
+        """True when the '<name> STD.tif' uncertainty image of image_set.py:236 exists."""
+        return self.path is not None and Path(str(self.path).removesuffix('.tif') + ' STD.tif').exists()
 
     def load_std_image(self, STD_data=None, bit64: Optional[bool] = False):
         std_array = None

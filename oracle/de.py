@@ -64,7 +64,7 @@ def trial_population(pop, seed, gen, dither, crossover, lower, upper):
 def select(pop, energies, trial, trial_energies, tol=0.01, atol=0.0):
     """Deferred selection, promotion of the best member to row 0 and scipy's convergence test."""
     pop, energies = np.array(pop, dtype=np.float64), np.array(energies, dtype=np.float64)
-    loc = np.asarray(trial_energies) < energies
+    loc = np.asarray(trial_energies) <= energies          # scipy _accept_trial (energy_trial <= energy_orig)
     pop = np.where(loc[:, None], trial, pop)
     energies = np.where(loc, trial_energies, energies)
     best = int(np.argmin(energies))

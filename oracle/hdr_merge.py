@@ -57,10 +57,16 @@ def flat_field_means(flat: np.ndarray, roi):
     return np.mean(flat[r0:r1, c0:c1, :], axis=(0, 1))     # measurand.py:579
 
 
-def normalize_by_map(val, std, flat_val, flat_std, roi):
-    """``measurand.py:559-604`` (flat-field correction with uncertainty), repair R7."""
-    m = flat_field_means(flat_val, roi)
-    ms = flat_field_means(flat_std, roi)
+def normalize_by_map(val, std, flat_val, flat_std, roi, means=None):
+    """``measurand.py:559-604`` (flat-field correction with uncertainty), repair R7.
+
+    ``means = (m, ms)`` overrides the ROI means -- used by the tests to check a ROW CROP of a large
+    image, where the ROI lies outside the crop and the means come from the full flat field."""
+    if means is None:
+        m = flat_field_means(flat_val, roi)
+        ms = flat_field_means(flat_std, roi)
+    else:
+        m, ms = means
 
     u_acq = (std ** 2) / (flat_val ** 2)
     u_acq *= m ** 2
@@ -79,7 +85,7 @@ def normalize_by_map(val, std, flat_val, flat_std, roi):
 
 def hdr_merge(dn_stack, std_stack, exposures, icrf, icrf_diff, *, max_dn: int = 255,
               darks=None, dark_threshold: float = 0.05, kernel: int = 3,
-              flat_val=None, flat_std=None, roi=None):
+              flat_val=None, flat_std=None, roi=None, flat_means=None):
     """Merge N exposures into an HDR radiance image with its uncertainty.
 
     dn_stack   : sequence of N integer images (H, W, C) -- what ``cv.imread`` returns
@@ -120,7 +126,7 @@ def hdr_merge(dn_stack, std_stack, exposures, icrf, icrf_diff, *, max_dn: int = 
     hdr_std = hdr_std ** (1 / 2)                                           # :394
 
     if flat_val is not None:
-        hdr_val, hdr_std = normalize_by_map(hdr_val, hdr_std, flat_val, flat_std, roi)
+        hdr_val, hdr_std = normalize_by_map(hdr_val, hdr_std, flat_val, flat_std, roi, flat_means)
     return hdr_val, hdr_std
 
 

@@ -110,3 +110,27 @@ def test_operators_on_device_match_the_unmodified_reference(golden_dir):
     from test_measurand_contract import _operator_results, check_operator_goldens
     g = np.load(golden_dir / "k8_operators.npz")
     check_operator_goldens(_operator_results(cl.Measurand, g, dev), g, 1e-13)
+
+
+def test_linearize_follows_the_thresholded_value_image():
+    """load -> apply_thresholds -> linearize must linearise the CURRENT measurand.val (thresholded
+    NaN wraps to ICRF[0], measurand.py:502-505), not the integers decoded from the file."""
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (16, 20, 3), dtype=np.uint8)
+    icrf, diff = icrf_tables(3)
+    s = cl.ImageSet(features=_features(0.01))
+    s.set_digital_numbers(img)
+    s.load_value_image()
+    assert s.dn is not None
+    before = s.linearize(icrf, diff)
+    ev, _ = ol.linearize(img, None, icrf, diff)
+    assert np.array_equal(host(before.measurand.val), ev)
+    s.measurand.apply_thresholds([0.2] * 3, [0.8] * 3)
+    assert s.dn is None
+    after = s.linearize(icrf, diff)
+    val = img.astype(np.float64) / 255
+    val[(val < 0.2) | (val > 0.8)] = np.nan
+    with np.errstate(invalid="ignore"):
+        ev2, _ = ol.linearize(val, None, icrf, diff)
+    assert np.array_equal(host(after.measurand.val), ev2)
+    assert not np.array_equal(ev, ev2)

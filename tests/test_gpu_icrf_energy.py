@@ -122,3 +122,32 @@ def test_full_size_cfg3_against_oracle_subset():
     np.testing.assert_allclose(acc[..., 0], halves[0][..., 0] + halves[1][..., 0], rtol=1e-12)
     ref = oe.energy_population(params[:, :3], mean, q, dn, None, 5, 250, True, t)
     assert_rel(e[:3], ref, TIGHT)
+
+
+def test_full_size_cfg3_with_std_against_oracle_subset():
+    """cfg3 WITH uncertainty stacks (S=64, 400k px x 5, inverse-sigma weighted pair means): pair sums are
+    linear in the pixels (whole = sum of two halves) and 3 candidates agree with the oracle on the full data."""
+    rng = np.random.default_rng(33)
+    x = np.linspace(0, 1, 256)
+    mean = x ** 2.2
+    q, _ = np.linalg.qr(np.stack([np.sin((k + 1) * np.pi * x) * x for k in range(5)], axis=1))
+    t = 0.005 * 2.0 ** np.arange(5)
+    rad = rng.uniform(0, 1, (1000, 400, 1)) * 25
+    dn = np.rint(255 * np.clip(rad * t[None, None, :], 0, 1) ** (1 / 2.2)).astype(np.uint8)
+    sd = rng.uniform(0.002, 0.02, dn.shape)
+    sd[::97, ::13, 2] = 0.0                       # sigma == 0 -> the pair is skipped (general_functions.py:165-170)
+    params = rng.uniform(-0.05, 0.05, (5, 64))
+    params[:, 9] = [0, 0, 0, 0, 2.0]              # gated
+    whole = cl.EnergyEvaluator(mean, q, dn, sd, 5, 250, True, t, 64, shard=False)
+    e = whole(params)
+    assert np.isinf(e[9]) and np.isfinite(np.delete(e, 9)).all()
+    acc = host(whole.plan.pair_acc).copy()
+    halves = []
+    for part, sp in ((dn[:500], sd[:500]), (dn[500:], sd[500:])):
+        ev = cl.EnergyEvaluator(mean, q, part, sp, 5, 250, True, t, 64, shard=False)
+        ev(params)
+        halves.append(host(ev.plan.pair_acc).copy())
+    live = np.arange(64) != 9                     # (a gated candidate's tables are all NaN)
+    np.testing.assert_allclose(acc[live], (halves[0] + halves[1])[live], rtol=1e-12)
+    ref = oe.energy_population(params[:, :3], mean, q, dn, sd, 5, 250, True, t)
+    assert_rel(e[:3], ref, TIGHT)

@@ -194,3 +194,43 @@ def test_de_oracle_step_properties():
         assert e2[0] == e2.min() == min(e.min(), te.min())
     u = ode.draw(1, 2, np.arange(100000), 3)
     assert 0.49 < u.mean() < 0.51 and u.min() >= 0 and u.max() < 1
+
+
+def test_decoded_integers_follow_the_current_value_image():
+    """ImageSet keeps the decoded integers next to ``measurand.val`` as a cache for the fused kernels.  The
+    reference always works from the CURRENT ``measurand.val`` (measurand.py:502-505), so the cache must die
+    when the value image is replaced, released (``val = None``) or modified in place (apply_thresholds)."""
+    img = np.arange(4 * 5 * 3, dtype=np.uint8).reshape(4, 5, 3)
+    with patch("cv2.imread", return_value=img):
+        s = ImageSet(file_path="5ms BF a 10x.tif")
+        s.load_value_image()
+    assert s.dn is not None and torch.equal(s.dn, torch.from_numpy(img))
+    assert torch.equal(s.digital_numbers(), torch.from_numpy(img))
+    # in-place modification through the Measurand API
+    s.measurand.apply_thresholds([0.1] * 3, [0.9] * 3)
+    assert s.dn is None
+    # re-loading gives a fresh, valid cache; assigning a new value image drops it again
+    with patch("cv2.imread", return_value=img):
+        s2 = ImageSet(file_path="5ms BF a 10x.tif")
+        s2.load_value_image()
+    s2.measurand.val = s2.measurand.val * 0.5
+    assert s2.dn is None
+    # releasing the image the reference's way releases the integers too
+    with patch("cv2.imread", return_value=img):
+        s3 = ImageSet(file_path="5ms BF a 10x.tif")
+        s3.load_value_image()
+    s3.measurand.val = None
+    assert s3.dn is None
+    with pytest.raises(ValueError):
+        s3.digital_numbers()
+    # in-memory integers attached without a value image stay valid until a value image appears
+    s4 = ImageSet(features={"illumination": "bf", "magnification": "10x", "exposure": 0.01, "subject": "s"})
+    s4.set_digital_numbers(img)
+    assert s4.dn is not None and s4.measurand.val is None
+    s4.measurand.val = torch.zeros((4, 5, 3), dtype=torch.float64)
+    assert s4.dn is None
+    # integer value image given to the constructor
+    s5 = ImageSet(value=img)
+    assert s5.dn is not None
+    s5.measurand = Measurand(img.astype(np.float64) / 255)
+    assert s5.dn is None
