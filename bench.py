@@ -69,6 +69,12 @@ def config_of(wl, world):
             "parallelism": f"independent stacks x{world}, no collective"}
 
 
+def std_table(C):
+    """Synthetic camera STD table (image_set.py:365-385): shot-noise-like, sigma grows with the signal."""
+    x = np.linspace(0, 1, 256)
+    return 0.002 + 0.018 * np.sqrt(x)[:, None] * np.array([1.0, 0.9, 1.1, 1.0])[:C]
+
+
 def algorithmic_bytes(wl, n_dark):
     n = wl["H"] * wl["W"] * wl["C"]
     b = wl["N"] * n * 9 + n_dark * n * 1 + n * 16
@@ -353,6 +359,32 @@ def run_ours(args, wl):
     pix_exp = wl["H"] * wl["W"] * wl["N"]
     value = world * pix_exp * args.steps / (total_ms * 1e-3) / 1e9
 
+    # ---- the same stack WITHOUT uncertainty images (sigma from the camera's STD table), device resident ----
+    std_lut_np = std_table(wl["C"])
+    std_lut_dev = torch.from_numpy(std_lut_np).to(dev)
+
+    def step_table():
+        means = None
+        if data["flat"] is not None:
+            means = ops.flat_roi_means(data["flat"], data["flat_std"], roi)
+        ops.hdr_merge(data["dn"], None, t, icrf, diff, std_lut=std_lut_dev, darks=data["darks"],
+                      dark_threshold=DARK_THRESHOLD, median_kernel=KERNEL, flat=data["flat"], flat_std=data["flat_std"],
+                      flat_means=means, algo=args.algo, out=out)
+
+    for _ in range(3):
+        step_table()
+    barrier()
+    ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ta.record()
+    for _ in range(args.steps):
+        step_table()
+    tb.record()
+    barrier()
+    tab_ms = torch.tensor([ta.elapsed_time(tb) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tab_ms, op=dist.ReduceOp.MAX)
+    tab_ms = float(tab_ms.item())
+
     # ---- e2e: public API from pinned host buffers, H2D + D2H inside the timed region ----
     # Every step uploads the N exposures (uint8 DNs + float64 uncertainty images) from pinned host memory,
     # merges them through ExposureSeries.process_HDR_image and reads the float64 radiance + uncertainty back.
@@ -377,14 +409,16 @@ def run_ours(args, wl):
     del out
     torch.cuda.empty_cache()
 
-    def e2e_step(out_host):
+    def e2e_step(out_host, use_table):
         sets = []
         for k in range(wl["N"]):
-            s = cl.ImageSet(features=feats(t[k], "s"), measurand=cl.Measurand(None, host["std"][k].to(dev, non_blocking=True)))
+            std_k = None if use_table else host["std"][k].to(dev, non_blocking=True)
+            s = cl.ImageSet(features=feats(t[k], "s"), measurand=cl.Measurand(None, std_k))
             s.set_digital_numbers(host["dn"][k])            # pinned host tensor -> device, asynchronous
             sets.append(s)
         series = cl.ExposureSeries(input_image_sets=sets)
-        series.process_HDR_image(icrf, diff, dark_list=dark_sets, flat_list=flats, algo=args.algo)
+        series.process_HDR_image(icrf, diff, dark_list=dark_sets, flat_list=flats, algo=args.algo,
+                                 STD_data=std_lut_dev if use_table else None)
         m = series.merged_image_set.measurand
         out_host[0].copy_(m.val, non_blocking=True)
         out_host[1].copy_(m.std, non_blocking=True)
@@ -396,28 +430,36 @@ def run_ours(args, wl):
     streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
     out_hosts = [out_host, (torch.empty_like(out_host[0]).pin_memory(), torch.empty_like(out_host[1]).pin_memory())]
 
-    def e2e_run(count):
+    def e2e_run(count, use_table):
         for i in range(count):
             with torch.cuda.stream(streams[i % 2]):
-                e2e_step(out_hosts[i % 2])
+                e2e_step(out_hosts[i % 2], use_table)
         for st in streams:
             st.synchronize()
 
-    e2e_run(2)
-    barrier()
-    wall0 = time.perf_counter()
-    e2e_run(n_e2e)
-    barrier()
-    e2e_ms = (time.perf_counter() - wall0) * 1e3
-    tm = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    e2e_value = world * pix_exp * n_e2e / (float(tm.item()) * 1e-3) / 1e9
-    n_samp = wl["H"] * wl["W"] * wl["C"]
-    h2d = wl["N"] * n_samp * 9
-    d2h = n_samp * 16
-    del host, dark_sets, flats, data
+    def e2e_measure(use_table):
+        e2e_run(2, use_table)
+        barrier()
+        wall0 = time.perf_counter()
+        e2e_run(n_e2e, use_table)
+        barrier()
+        ms = (time.perf_counter() - wall0) * 1e3
+        tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm.item())
 
+    n_samp = wl["H"] * wl["W"] * wl["C"]
+    d2h = n_samp * 16
+    e2e_total_ms = e2e_measure(False)
+    e2e_value = world * pix_exp * n_e2e / (e2e_total_ms * 1e-3) / 1e9
+    h2d = wl["N"] * n_samp * 9
+    # the same stack WITHOUT uncertainty images: sigma = STD_data[DN, c] (image_set.py:228-243, 365-385, the
+    # reference's path whenever no '... STD.tif' exists) -> only the uint8 exposures cross PCIe
+    e2e_tab_ms = e2e_measure(True)
+    e2e_tab_value = world * pix_exp * n_e2e / (e2e_tab_ms * 1e-3) / 1e9
+    h2d_tab = wl["N"] * n_samp
+    del host, dark_sets, flats, data
     extra = {}
     if rank == 0 and not args.no_extra:
         try:
@@ -449,13 +491,24 @@ def run_ours(args, wl):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "Gpix*exposures/s", "h2d_bytes_per_step": world * h2d,
                 "d2h_bytes_per_step": world * d2h,
-                "ms_per_step": float(tm.item()) / n_e2e, "steps": n_e2e,
+                "ms_per_step": e2e_total_ms / n_e2e, "steps": n_e2e,
                 "api": "ExposureSeries.process_HDR_image on ImageSets built from pinned host tensors (ImageSet.set_digital_numbers "
                        "+ Measurand std); every step uploads the 16 exposures (uint8 + float64 uncertainty images) and reads the "
                        "float64 result back; the dark frames and the flat field are per-camera calibration frames, uploaded once "
                        "and kept resident; steps alternate between two CUDA streams (D2H of step i overlaps H2D of step i+1); "
                        "wall-clock timed",
                 "numa_bound": bool(numa_bound)},
+        "std_table_variant": {
+            "what": "the same stack without uncertainty images: sigma = STD_data[DN, c] gathered inside the merge kernel "
+                    "(image_set.py:228-243, 365-385 -- the reference's path whenever no '... STD.tif' exists)",
+            "value": world * pix_exp / (tab_ms * 1e-3) / 1e9, "unit": "Gpix*exposures/s", "ms_per_step": tab_ms,
+            "algorithmic_bytes_per_step": alg_bytes - wl["N"] * n_samp * 8,
+            "bound": "sm (shared-memory table gathers + FP64), not HBM: "
+                     f"{(alg_bytes - wl['N'] * n_samp * 8) / tab_ms / 1e6:.0f} GB/s of algorithmic traffic",
+            "e2e": {"value": e2e_tab_value, "unit": "Gpix*exposures/s", "h2d_bytes_per_step": world * h2d_tab,
+                    "d2h_bytes_per_step": world * d2h, "ms_per_step": e2e_tab_ms / n_e2e, "steps": n_e2e,
+                    "api": "as `e2e`, with ExposureSeries.process_HDR_image(STD_data=...) and no uncertainty images: only "
+                           "the uint8 exposures cross PCIe"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "extra": extra,

@@ -707,8 +707,10 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
     }
     int algo = a->algo;
     const bool staged_ok = merge_staged_supported(p, all_std);
-    if (algo == 0) algo = staged_ok ? 2 : 1;
+    const bool staged_lut_ok = !staged_ok && merge_staged_lut_supported(p);   // no uncertainty images: STD table
+    if (algo == 0) algo = (staged_ok || staged_lut_ok) ? 2 : 1;
     if (algo == 2) {
+        if (staged_lut_ok) return launch_merge_staged_lut(p, s);
         if (!staged_ok) return CL_ERR_UNSUPPORTED;
         return launch_merge_staged(p, s);
     }

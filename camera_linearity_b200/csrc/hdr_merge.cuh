@@ -70,6 +70,20 @@ __device__ __forceinline__ void merge_accumulate(double w, double p1, double dgl
     acc_val = fma(p1, rt, acc_val);
 }
 
+// The same contribution when sigma comes from the camera's STD table (a function of the DN): the caller has
+// tabulated  X = fma(w*dgl, sigma, kappa*p1)  and  Y0 = dgl*sigma  per DN with the operations above, what is left
+// per exposure is below -- every intermediate is the bit pattern merge_accumulate() produces.
+__device__ __forceinline__ void merge_accumulate_lut(double w, double p1, double X, double Y0, double kappa,
+                                                     double rS, double rt, double& acc_val, double& acc_var) {
+    const double a = kappa * p1;        // dw * g
+    const double e = a * w;             // dw * w * g
+    const double z = fma(-e, rS, X);
+    const double y = Y0 * rt;
+    const double q = z * y;
+    acc_var = fma(q, q, acc_var);
+    acc_val = fma(p1, rt, acc_val);
+}
+
 __device__ __forceinline__ double kappa_of(uint32_t d, double kappa_scale) {
     return fma(u32_to_double(d), kappa_scale, 30.0);
 }
@@ -207,6 +221,8 @@ __device__ __forceinline__ double flat_recip(const void* flat, int flat_bytes, i
 }
 
 int launch_merge_staged(const MergeParams& p, cudaStream_t stream);   // hdr_merge_staged.cu
+int launch_merge_staged_lut(const MergeParams& p, cudaStream_t stream);   // hdr_merge_staged_lut.cu
+bool merge_staged_lut_supported(const MergeParams& p);
 int launch_merge_wide(const MergeParams& p, cudaStream_t stream);     // hdr_merge_wide.cu
 bool merge_wide_supported(const MergeParams& p, int dn_bytes, bool all_std_images);
 size_t wide_table_bytes(int bits, int C);
