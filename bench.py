@@ -460,6 +460,12 @@ def run_ours(args, wl):
     e2e_tab_value = world * pix_exp * n_e2e / (e2e_tab_ms * 1e-3) / 1e9
     h2d_tab = wl["N"] * n_samp
     del host, dark_sets, flats, data
+    k4 = None
+    if not args.no_extra:
+        try:
+            k4 = k4_block(dev, rank, world, cpu=not args.no_cpu)
+        except Exception as exc:
+            k4 = {"error": repr(exc)}
     extra = {}
     if rank == 0 and not args.no_extra:
         try:
@@ -509,11 +515,95 @@ def run_ours(args, wl):
                     "d2h_bytes_per_step": world * d2h, "ms_per_step": e2e_tab_ms / n_e2e, "steps": n_e2e,
                     "api": "as `e2e`, with ExposureSeries.process_HDR_image(STD_data=...) and no uncertainty images: only "
                            "the uint8 exposures cross PCIe"}},
+        "k4_icrf_fit": k4,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "extra": extra,
     }
     print(json.dumps(line))
+
+
+def cfg3_problem():
+    """cfg3 of BASELINE.json / SURVEY 8d: 400 000 pixels x 5 exposures (4.0 M pixel-pairs per evaluation), 64 candidates
+    over 5 principal components (an all-valid population: most random candidates of a wide box hit the +inf gates)."""
+    x = np.linspace(0, 1, 256)
+    modes = np.stack([np.sin((k + 1) * np.pi * x) * x for k in range(5)], axis=1)
+    pca, _ = np.linalg.qr(modes)
+    rng = np.random.default_rng(3)
+    tt = 0.005 * 2.0 ** np.arange(5)
+    rad = rng.uniform(0, 1, (1000, 400, 1)) * 25
+    stack = np.rint(255 * np.clip(rad * tt[None, None, :], 0, 1) ** (1 / 2.2)).astype(np.uint8)
+    std = rng.uniform(0.002, 0.02, stack.shape)
+    params = rng.uniform(-0.05, 0.05, (5, 64))
+    return x ** 2.2, pca, tt, stack, std, params
+
+
+def k4_block(dev, rank, world, cpu=True):
+    """ICRF-fit loss evaluations per second on cfg3 with the pixels sharded over the `world` GPUs (collective: every
+    rank calls it).  `population`: candidate curves + partial kernel + fused tail (CTA reduction, pair sums exchanged
+    through peer memory, finalize) timed with CUDA events, max over ranks.  `de_generation`: the same inside the
+    device-resident DE (4 launches per generation, 8 generations per CUDA-graph replay)."""
+    import torch
+    import torch.distributed as dist
+    import camera_linearity_b200 as cl
+    from camera_linearity_b200 import ops
+    from scipy.stats import qmc
+    mean, pca, tt, stack, std, params = cfg3_problem()
+    out = {"shape": "cfg3: S=64 candidates x 5 PCs, 400k px x 5 exposures (4.0M pixel-pairs per eval), pixels sharded "
+                    f"over {world} GPU(s)", "unit": "evals/s"}
+
+    def sync_max(ms):
+        tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm.item())
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return sync_max(a.elapsed_time(b) / reps)
+
+    for name, sdv in (("nostd", None), ("std", std)):
+        ev = cl.EnergyEvaluator(mean, pca, stack, sdv, 5, 250, True, tt, 64, shard=True)
+        p_dev = torch.from_numpy(np.ascontiguousarray(params.T)).to(dev)
+        ms = timed(lambda: ev.device_energies(p_dev), reps=50)
+        res = {"ms_per_population": ms, "evals/s": 64e3 / ms, "pair_evals/s": 64 * 400000 * 10 / ms * 1e3,
+               "exchange": ev.exchange, "launches_per_population": 3 if ev.exchange != "nccl" else 5}
+        unit = qmc.Sobol(d=5, seed=np.random.default_rng(7)).random(n=64)
+        if ev.exchange != "nccl":
+            de = ops.DeviceDE.for_plan(ev.plan, [-0.5] * 5, [0.5] * 5, torch.from_numpy(unit).to(dev), seed=7, tol=0.0)
+            de.run_graph(8, per_graph=8)
+            gen_ms = timed(lambda: de.run_graph(8, per_graph=8), reps=12, warm=2) / 8
+            res["de_generation"] = {"ms": gen_ms, "evals/s": 64e3 / gen_ms, "generations/s": 1e3 / gen_ms,
+                                    "how": "cl_de_trial_curves + partial + fused tail + cl_de_select, CUDA graph of 8 generations"}
+        else:
+            de = ops.DeviceDE(ev.device_energies, [-0.5] * 5, [0.5] * 5, torch.from_numpy(unit).to(dev), seed=7, tol=0.0)
+            gen_ms = timed(de.step, reps=40, warm=3)
+            res["de_generation"] = {"ms": gen_ms, "evals/s": 64e3 / gen_ms, "generations/s": 1e3 / gen_ms,
+                                    "how": "generic step with an NCCL all-reduce between partial and finalize"}
+        out[name] = res
+        del ev, de
+    if cpu and rank == 0:
+        # the reference's objective (oracle port of _energy_function, ICRF_calibration_exposure.py:148-201) on the same
+        # pixels, one host core, a bounded number of candidates
+        from oracle import icrf_energy as oe
+        for name, sdv, n_cand in (("nostd", None, 3), ("std", std, 2)):
+            t0 = time.perf_counter()
+            oe.energy_population(params[:, :n_cand], mean, pca, stack, sdv, 5, 250, True, tt)
+            dt = time.perf_counter() - t0
+            out[name]["cpu_baseline"] = {"value": n_cand / dt, "unit": "evals/s", "cores": 1, "kind": "port",
+                                         "sample": f"{n_cand} candidates of the population on the full 400k px x 5 stack, "
+                                                   f"NumPy port of _energy_function, {dt:.2f} s"}
+    return out
 
 
 def extra_kernels(dev):
@@ -603,55 +693,17 @@ def extra_kernels(dev):
                                "shape": "cfg4: 600x1080x1920x3 u8"}
     ms = timed(lambda: ops.welford_stack(frames, icrf, 255.0, ws), reps=3, warm=1)       # linearised frames (ICRF given)
     out["k3_welford_stack_icrf"] = {"ms": ms, "GB/s": nb / ms / 1e6, "shape": "cfg4 with ICRF[frame, c] as the sample value"}
+    # the reference's Welford recurrence (oracle port of video_processing.py:183-217) on a bounded number of frames
+    from oracle import welford as ow
+    n_f = 12
+    host_frames = [f.cpu().numpy() for f in frames[:n_f]]
+    t0 = time.perf_counter()
+    ow.welford(host_frames)
+    dt = time.perf_counter() - t0
+    out["k3_welford_stack"]["cpu_baseline"] = {"value": n_f * 1080 * 1920 / dt / 1e9, "unit": "Gpix*frames/s", "cores": 1,
+                                               "kind": "port", "sample": f"{n_f} frames 1080x1920x3, NumPy port of "
+                                                                         f"welford_algorithm, {dt:.2f} s"}
     del frames, ws
-    # K4: cfg3, S=64 candidates, 400k px x 5 exposures
-    x = np.linspace(0, 1, 256)
-    modes = np.stack([np.sin((k + 1) * np.pi * x) * x for k in range(5)], axis=1)
-    pca, _ = np.linalg.qr(modes)
-    rng = np.random.default_rng(3)
-    tt = 0.005 * 2.0 ** np.arange(5)
-    rad = rng.uniform(0, 1, (1000, 400, 1)) * 25
-    stack = np.rint(255 * np.clip(rad * tt[None, None, :], 0, 1) ** (1 / 2.2)).astype(np.uint8)
-    std = rng.uniform(0.002, 0.02, stack.shape)
-    params = rng.uniform(-0.05, 0.05, (5, 64))
-    for name, sdv in (("nostd", None), ("std", std)):
-        ev = cl.EnergyEvaluator(x ** 2.2, pca, stack, sdv, 5, 250, True, tt, 64, shard=False)
-        plan = ev.plan
-        plan.set_params(torch.from_numpy(np.ascontiguousarray(params.T)))
-
-        def one():
-            plan.curves_and_tables()
-            plan.partial()
-            plan.finalize()
-        ms = timed(one, reps=10, warm=2)
-        out[f"k4_icrf_energy_{name}"] = {"ms_per_population": ms, "evals/s": 64 / ms * 1e3,
-                                         "pair_evals/s": 64 * 400000 * 10 / ms * 1e3,
-                                         "shape": "cfg3: S=64, 400k px x 5 exposures (4.0M pixel-pairs per eval)"}
-    # DE generations per second on cfg3 (no std): scipy's host loop around the GPU objective vs the
-    # device-resident generation (cl_de_trial -> K4 -> cl_de_select, no host round trip)
-    import time
-    from scipy.optimize._differentialevolution import DifferentialEvolutionSolver
-    from scipy.stats import qmc
-    ev = cl.EnergyEvaluator(x ** 2.2, pca, stack, None, 5, 250, True, tt, 64, shard=False)
-    gens = 60
-    limits = [[-0.5, 0.5]] * 5
-    with DifferentialEvolutionSolver(lambda pop: ev(np.asarray(pop)), limits, strategy='currenttobest1bin', tol=0.0,
-                                     x0=[0.0] * 5, mutation=(0, 1.95), recombination=0.4, init='sobol', rng=7,
-                                     popsize=12, vectorized=True, updating='deferred', polish=False) as solver:
-        for _ in range(5):
-            next(solver)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(gens):
-            next(solver)
-        torch.cuda.synchronize()
-        host_ms = (time.perf_counter() - t0) / gens * 1e3
-    unit = qmc.Sobol(d=5, seed=np.random.default_rng(7)).random(n=64)
-    de = ops.DeviceDE(ev.device_energies, [-0.5] * 5, [0.5] * 5, torch.from_numpy(unit).to(dev), seed=7, tol=0.0)
-    dev_ms = timed(de.step, reps=gens, warm=5)
-    out["k4_de_generation"] = {"scipy_host_loop_ms": host_ms, "device_resident_ms": dev_ms,
-                               "generations/s_device": 1e3 / dev_ms, "evals/s_device": 64e3 / dev_ms,
-                               "shape": "cfg3 without std, 64 members x 5 parameters"}
     return out
 
 

@@ -35,7 +35,10 @@ class EnergyEvaluator:
     """Population objective for one colour channel, resident on this rank's GPU."""
 
     def __init__(self, mean_ICRF, PCA_array, image_value_stack, image_std_stack, lower, upper, use_mean,
-                 exposure_values, n_candidates: int, shard: bool = True):
+                 exposure_values, n_candidates: int, shard: bool = True, exchange: str = "auto"):
+        """shard: split the pixels over the ranks of the process group.  exchange: how the ranks' pair sums meet --
+        "peer" (pushed through peer memory inside the fused tail kernel), "nccl" (all-reduce between the partial and
+        finalize launches) or "auto" (peer when every rank has its own GPU, else nccl)."""
         dev = gs.device()
         dn = torch.as_tensor(image_value_stack)
         if dn.dtype.is_floating_point:
@@ -55,6 +58,17 @@ class EnergyEvaluator:
                                        mean_ICRF, torch.as_tensor(np.asarray(PCA_array), device=dev),
                                        int(lower), int(upper), bool(use_mean), int(n_candidates))
         self.sharded = shard and parallel.world_size() > 1
+        self.exchange = "none"
+        if self.sharded:
+            if exchange == "auto":
+                exchange = "peer" if torch.cuda.device_count() >= parallel.world_size() else "nccl"
+            if exchange not in ("peer", "nccl"):
+                raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+            self.exchange = exchange
+            if exchange == "peer":
+                nbytes = self.plan.lib.cl_icrf_exchange_bytes(self.plan.prob, parallel.world_size())
+                self._peers = parallel.PeerExchange(nbytes)
+                self.plan.attach_peers(self._peers)
 
     def __call__(self, params):
         """params: (n_params,) or (n_params, S) NumPy array -> float or (S,) NumPy array."""
@@ -64,12 +78,7 @@ class EnergyEvaluator:
         plan = self.plan
         if pop.shape[0] != plan.n_real:
             raise ValueError(f"evaluator was built for {plan.n_real} candidates, got {pop.shape[0]}")
-        plan.set_params(torch.from_numpy(np.ascontiguousarray(pop)))
-        plan.curves_and_tables()
-        acc = plan.partial()
-        if self.sharded:
-            parallel.allreduce_pair_sums(acc)
-        e = plan.finalize().cpu().numpy()
+        e = self.device_energies(torch.from_numpy(np.ascontiguousarray(pop))).cpu().numpy()
         return float(e[0]) if single else e
 
     def device_energies(self, params: torch.Tensor) -> torch.Tensor:
@@ -78,10 +87,10 @@ class EnergyEvaluator:
         plan = self.plan
         plan.set_params(params)
         plan.curves_and_tables()
-        acc = plan.partial()
-        if self.sharded:
-            parallel.allreduce_pair_sums(acc)
-        return plan.finalize()
+        if self.exchange == "nccl":
+            parallel.allreduce_pair_sums(plan.partial())
+            return plan.finalize()
+        return plan.population()          # single rank, or peer-memory exchange inside the tail kernel
 
 
 def _energy_function(PCA_params, mean_ICRF, PCA_array, image_value_stack, image_std_stack, lower, upper,
@@ -147,13 +156,22 @@ def _solve_channel_device(mean_ICRF, PCA_array, image_value_stack, image_std_sta
     unit[0] = (np.asarray(x0, dtype=np.float64) - arg1) / arg2 + 0.5
     evaluator = EnergyEvaluator(mean_ICRF, PCA_array, image_value_stack, image_std_stack, data_limits[0],
                                 data_limits[1], use_mean_ICRF, exposure_values, members)
-    de = ops.DeviceDE(evaluator.device_energies, lower, upper, torch.from_numpy(unit).to(gs.device()), seed)
+    # single rank / peer-memory exchange: the fused generation (4 launches) replayed from a CUDA graph;
+    # NCCL exchange: the generic step with the all-reduce between the partial and finalize launches
+    fused = evaluator.exchange != "nccl"
+    if fused:
+        de = ops.DeviceDE.for_plan(evaluator.plan, lower, upper, torch.from_numpy(unit).to(gs.device()), seed)
+    else:
+        de = ops.DeviceDE(evaluator.device_energies, lower, upper, torch.from_numpy(unit).to(gs.device()), seed)
     iterations = 0
     energy = float("inf")
     while iterations < max_iterations:
         burst = min(check_every, max_iterations - iterations)
-        for _ in range(burst):
-            de.step()
+        if fused and burst == check_every:
+            de.run_graph(burst, per_graph=check_every)
+        else:
+            for _ in range(burst):
+                de.step_fused() if fused else de.step()
         converged, iterations, energy = de.poll()
         if converged or energy < energy_limit:
             break

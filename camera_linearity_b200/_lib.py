@@ -51,6 +51,19 @@ class IcrfProblem(C.Structure):
     ]
 
 
+CL_MAX_PEERS = 16
+
+
+class PeerGroup(C.Structure):
+    """``cl_peer_group`` (include/camera_linearity.h)."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("buffers", C.c_void_p * CL_MAX_PEERS)]
+
+
+class IpcHandle(C.Structure):
+    """``cl_ipc_handle`` (include/camera_linearity.h)."""
+    _fields_ = [("bytes", C.c_ubyte * 64)]
+
+
 _vp, _i, _i64, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t
 
 # name -> (restype, argtypes); every symbol include/camera_linearity.h declares
@@ -77,6 +90,15 @@ SIGNATURES = {
     "cl_icrf_energy_partial": (_i, [C.POINTER(IcrfProblem), _vp, _vp, _vp, C.POINTER(C.c_double),
                                     _i64, _vp, _vp, _sz, _vp]),
     "cl_icrf_energy_finalize": (_i, [C.POINTER(IcrfProblem), _vp, _vp, _vp, _vp]),
+    "cl_icrf_exchange_bytes": (_sz, [C.POINTER(IcrfProblem), _i]),
+    "cl_icrf_energy_population": (_i, [C.POINTER(IcrfProblem), _vp, _vp, _vp, C.POINTER(C.c_double), _i64, _vp, _vp,
+                                       _vp, _vp, _sz, C.POINTER(PeerGroup), _vp]),
+    "cl_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p), C.POINTER(IpcHandle)]),
+    "cl_peer_open": (_i, [C.POINTER(IpcHandle), C.POINTER(C.c_void_p)]),
+    "cl_peer_close": (_i, [_vp]),
+    "cl_peer_free": (_i, [_vp]),
+    "cl_de_trial_curves": (_i, [C.POINTER(IcrfProblem), _vp, _i, _d, _d, _d, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _vp, _vp, _vp, _vp, _vp]),
     "cl_channel_histogram": (_i, [_vp, _vp, _i64, _i, _i, _i, _d, _d, _vp, _vp, _vp]),
     "cl_de_trial": (_i, [_vp, _i, _i, _d, _d, _d, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cl_de_select": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp]),

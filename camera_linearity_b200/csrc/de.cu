@@ -14,57 +14,19 @@
 // (seed, generation, candidate, slot), so the stream does not depend on the launch geometry and
 // oracle/de.py reproduces it bit for bit.  The search is therefore statistically, not bitwise, the one
 // SciPy would run (tests compare both drivers' optima).
-#include "common.cuh"
+#include "de_common.cuh"
 
 namespace cl {
 namespace {
 
-__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
-}
-
-// draw `slot` of candidate `i` in generation `gen`: uniform double in [0, 1) with 53 random bits
-__host__ __device__ __forceinline__ double draw(uint64_t seed, uint64_t gen, uint32_t i, uint32_t slot) {
-    const uint64_t key = splitmix64(seed ^ (gen * 0xD1342543DE82EF95ull));
-    const uint64_t z = splitmix64(key + (((uint64_t)i << 8) | slot));
-    return (double)(z >> 11) * 0x1.0p-53;
-}
-
-constexpr uint32_t kSlotR0 = 0, kSlotR1 = 1, kSlotFill = 2, kSlotCross = 3;     // then P crossover, P redraw slots
-constexpr uint32_t kScaleCandidate = 0xFFFFFFFFu;                               // the per-generation dither draw
-
 // one thread per (candidate, parameter)
-__global__ void de_trial_kernel(const double* __restrict__ pop, int S, int P, double dither_lo, double dither_hi,
-                                double crossover, uint64_t seed, const int64_t* __restrict__ generation,
-                                const double* __restrict__ lo, const double* __restrict__ hi,
-                                double* __restrict__ trial, double* __restrict__ params) {
+__global__ void de_trial_kernel(const double* __restrict__ pop, int S, int P, const de::TrialConfig cfg,
+                                const int64_t* __restrict__ generation, const double* __restrict__ lo,
+                                const double* __restrict__ hi, double* __restrict__ trial, double* __restrict__ params) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= S * P) return;
     const int i = t / P, j = t - i * P;
-    const uint64_t gen = (uint64_t)generation[0];
-    const double scale = dither_lo + (dither_hi - dither_lo) * draw(seed, gen, kScaleCandidate, 0);
-    // two distinct members, both different from i
-    int r0 = (int)(draw(seed, gen, i, kSlotR0) * (double)(S - 1));
-    if (r0 >= i) ++r0;
-    int r1 = (int)(draw(seed, gen, i, kSlotR1) * (double)(S - 2));
-    const int a = i < r0 ? i : r0, b = i < r0 ? r0 : i;
-    if (r1 >= a) ++r1;
-    if (r1 >= b) ++r1;
-    const int fill = (int)(draw(seed, gen, i, kSlotFill) * (double)P);
-    const double xi = pop[i * P + j];
-    double v = xi;
-    if (j == fill || draw(seed, gen, i, kSlotCross + j) < crossover) {
-        // same association as SciPy: x_i + scale * (((x_best - x_i) + x_r0) - x_r1), unfused
-        const double d = __dsub_rn(__dadd_rn(__dsub_rn(pop[j], xi), pop[r0 * P + j]), pop[r1 * P + j]);
-        v = __dadd_rn(xi, __dmul_rn(scale, d));
-    }
-    if (v > 1.0 || v < 0.0) v = draw(seed, gen, i, kSlotCross + P + j);          // _ensure_constraint
-    trial[t] = v;
-    // _scale_parameters: 0.5 (lo + hi) + (x - 0.5) |hi - lo|
-    params[t] = __dadd_rn(__dmul_rn(0.5, __dadd_rn(lo[j], hi[j])), __dmul_rn(__dsub_rn(v, 0.5), fabs(__dsub_rn(hi[j], lo[j]))));
+    de::trial_component(pop, S, P, cfg, (uint64_t)generation[0], i, j, lo, hi, trial[t], params[t]);
 }
 
 // single block: selection, promotion of the best member to row 0, convergence test, generation counter
@@ -145,9 +107,9 @@ int cl_de_trial(const double* pop, int n_members, int n_params, double dither_lo
     CL_REQUIRE(n_members >= 4 && n_params >= 1 && n_params <= 64);
     CL_REQUIRE(dither_lo <= dither_hi && crossover >= 0.0 && crossover <= 1.0);
     const int n = n_members * n_params;
-    de_trial_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pop, n_members, n_params, dither_lo, dither_hi,
-                                                                      crossover, seed, generation, lower, upper,
-                                                                      trial, params);
+    const de::TrialConfig cfg{dither_lo, dither_hi, crossover, seed};
+    de_trial_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pop, n_members, n_params, cfg, generation, lower,
+                                                                      upper, trial, params);
     return launched();
 }
 

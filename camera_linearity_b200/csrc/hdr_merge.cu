@@ -404,7 +404,8 @@ template <int CT>
 __global__ void __launch_bounds__(kRoiThreads, CT ? 3 : 1)
 roi_partial_kernel(const void* __restrict__ flat, int flat_bytes, double max_dn,
                    const double* __restrict__ flat_std, int W, int C_rt, int r0, int c0, int rh, int rw,
-                   double* __restrict__ partial) {
+                   double* __restrict__ partial, unsigned int* __restrict__ ticket, double count,
+                   double* __restrict__ out) {
     // block b reduces ROI pixels [b*chunk, (b+1)*chunk) for every channel, fixed order
     constexpr int CM = CT ? CT : CL_MAX_CHANNELS;
     constexpr int kPix = 4;
@@ -466,18 +467,25 @@ roi_partial_kernel(const void* __restrict__ flat, int flat_bytes, double max_dn,
         for (int w = 0; w < kRoiThreads / 32; ++w) s += red[w][threadIdx.x];
         partial[(int64_t)blockIdx.x * 2 * C + threadIdx.x] = s;
     }
-}
-
-// one warp per output (2C warps): lanes stride over the per-block partials, fixed-order tree
-__global__ void roi_final_kernel(const double* __restrict__ partial, int n_blocks, int C,
-                                 double count, double* __restrict__ out) {
-    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (c >= 2 * C) return;
-    double s = 0.0;
+    // The block that draws the last ticket combines all partials -- in a FIXED order (lanes stride over the
+    // blocks, then an xor tree), so the result does not depend on which block that is.  One launch instead of
+    // two: the second kernel cost as much as the first (7.6 us of launch + latency for 2C numbers).
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (warp < 2 * C) {                                   // kRoiThreads / 32 = 8 warps >= 2C for C <= 4
+        for (int c = warp; c < 2 * C; c += kRoiThreads / 32) {
+            double s = 0.0;
 #pragma unroll 8
-    for (int b = lane; b < n_blocks; b += 32) s += partial[(int64_t)b * 2 * C + c];
-    s = warp_sum(s);
-    if (lane == 0) out[c] = s / count;
+            for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(partial + (int64_t)b * 2 * C + c);
+            s = warp_sum(s);
+            if (lane == 0) out[c] = s / count;
+        }
+    }
 }
 
 constexpr int kRoiBlocks = 444;      // 148 SMs x 3 resident blocks; fixed so the summation order is machine-independent
@@ -721,7 +729,7 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
 
 size_t cl_flat_roi_means_workspace_bytes(int height, int width, int channels) {
     (void)height; (void)width;
-    return (size_t)cl::kRoiBlocks * 2 * (channels > 0 ? channels : 1) * sizeof(double);
+    return (size_t)cl::kRoiBlocks * 2 * (channels > 0 ? channels : 1) * sizeof(double) + 16;   // partials + ticket
 }
 
 int cl_flat_roi_means(const void* flat, int flat_bytes, double max_dn, const double* flat_std,
@@ -742,12 +750,12 @@ int cl_flat_roi_means(const void* flat, int flat_bytes, double max_dn, const dou
     double* partial = reinterpret_cast<double*>(workspace);
     // an empty ROI yields 0/0 = NaN, like np.mean of an empty slice
     auto partial_kernel = channels == 3 ? roi_partial_kernel<3> : channels == 1 ? roi_partial_kernel<1> : roi_partial_kernel<0>;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + (size_t)kRoiBlocks * 2 * channels);
+    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return cuda_status(e);
     partial_kernel<<<kRoiBlocks, kRoiThreads, 0, s>>>(flat, flat_bytes, max_dn, flat_std, width, channels, r0, c0,
-                                                     rw > 0 ? rh : 0, rw > 0 ? rw : 1, partial);
-    int st = launched();
-    if (st != CL_OK) return st;
-    roi_final_kernel<<<1, 64 * CL_MAX_CHANNELS, 0, s>>>(partial, kRoiBlocks, channels, (double)rh * (double)rw,
-                                      out_means);
+                                                     rw > 0 ? rh : 0, rw > 0 ? rw : 1, partial, ticket,
+                                                     (double)rh * (double)rw, out_means);
     return launched();
 }
 

@@ -421,6 +421,20 @@ class IcrfEnergyPlan:
         self.energy = torch.empty(s_pad, **f64)
         self.ws_bytes = self.lib.cl_icrf_energy_workspace_bytes(C.byref(self.prob), self.n_pixels)
         self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev)
+        # exchange buffer of the fused tail (generation counter + ticket; with peers: the slots the other
+        # ranks push their pair sums into).  Single rank: a private zeroed buffer.
+        self._own_exchange = torch.zeros(self.lib.cl_icrf_exchange_bytes(C.byref(self.prob), 1), dtype=torch.uint8,
+                                         device=dev)
+        self.peers = _lib.PeerGroup()
+        self.peers.world, self.peers.rank = 1, 0
+        self.peers.buffers[0] = self._own_exchange.data_ptr()
+        self._peer_keepalive = None
+
+    def attach_peers(self, exchange) -> None:
+        """Use the peer-memory exchange of ``parallel.PeerExchange`` (one buffer per rank, mapped on this device):
+        ``population()`` then sums the pair sums of all ranks inside its tail kernel."""
+        self.peers = exchange.peer_group()
+        self._peer_keepalive = exchange
 
     def set_params(self, params: Tensor) -> None:
         """params: (S, n_params) -- one row per candidate (device or host)."""
@@ -445,12 +459,22 @@ class IcrfEnergyPlan:
                                                _ptr(self.energy), _stream()), "cl_icrf_energy_finalize")
         return self.energy[: self.n_real]
 
+    def population(self) -> Tensor:
+        """Partial kernel + fused tail (CTA reduction, exchange with the attached peers, finalize): the energies
+        of the candidates whose curves / tables are current, over the pixels of ALL ranks."""
+        if self.n_pixels == 0:
+            raise ValueError("population() needs at least one pixel on every rank")
+        check(self.lib.cl_icrf_energy_population(C.byref(self.prob), _ptr(self.tables), _ptr(self.dn), _ptr(self.std),
+                                                 self.exposures, self.n_pixels, _ptr(self.valid), _ptr(self.pair_acc),
+                                                 _ptr(self.energy), _ptr(self.ws), self.ws_bytes, C.byref(self.peers),
+                                                 _stream()), "cl_icrf_energy_population")
+        return self.energy[: self.n_real]
+
     def evaluate(self, params) -> Tensor:
-        """Energies (S,) of a population on this GPU's pixels (single-GPU path)."""
+        """Energies (S,) of a population (over the pixels of all attached ranks)."""
         self.set_params(params)
         self.curves_and_tables()
-        self.partial()
-        return self.finalize()
+        return self.population()
 
 
 class DeviceDE:
@@ -493,6 +517,53 @@ class DeviceDE:
         check(self.lib.cl_de_select(_ptr(self.pop), _ptr(self.energies), _ptr(self.trial), _ptr(trial_energies),
                                     self.S, self.P, self.tol, self.atol, _ptr(self.generation), _ptr(self.status),
                                     _ptr(self.best), _stream()), "cl_de_select")
+
+    # ---- fused generation on an IcrfEnergyPlan: 4 launches, capturable in a CUDA graph ----
+    @classmethod
+    def for_plan(cls, plan: "IcrfEnergyPlan", lower, upper, init_unit_population: Tensor, seed: int, **kw):
+        """DE whose objective is ``plan`` (K4).  One generation = ``cl_de_trial_curves`` (trial vectors + candidate
+        curves), ``cl_icrf_energy_population`` (partial kernel + fused reduce / peer exchange / finalize) and
+        ``cl_de_select``: four kernels, no NCCL launch, nothing on the host."""
+        if plan.n_real != init_unit_population.shape[0] or plan.prob.n_params != init_unit_population.shape[1]:
+            raise ValueError("the plan must be built for exactly this population")
+        self = cls(lambda params: plan.evaluate(params), lower, upper, init_unit_population, seed, **kw)
+        self.plan = plan
+        self._graph = None
+        self._graph_steps = 0
+        return self
+
+    def step_fused(self) -> None:
+        plan = self.plan
+        check(self.lib.cl_de_trial_curves(C.byref(plan.prob), _ptr(self.pop), self.S, float(self.dither[0]),
+                                          float(self.dither[1]), self.cr, self.seed, _ptr(self.generation),
+                                          _ptr(self.lower), _ptr(self.upper), _ptr(self.trial), _ptr(plan.params),
+                                          _ptr(plan.mean), _ptr(plan.pca), _ptr(plan.curves), _ptr(plan.valid),
+                                          _ptr(plan.tables), _stream()), "cl_de_trial_curves")
+        trial_energies = plan.population()
+        check(self.lib.cl_de_select(_ptr(self.pop), _ptr(self.energies), _ptr(self.trial), _ptr(trial_energies),
+                                    self.S, self.P, self.tol, self.atol, _ptr(self.generation), _ptr(self.status),
+                                    _ptr(self.best), _stream()), "cl_de_select")
+
+    def run_graph(self, generations: int, per_graph: int = 8) -> None:
+        """Advance ``generations`` generations (a multiple of ``per_graph``) by replaying a CUDA graph of
+        ``per_graph`` fused generations: every pointer and the generation counter live on the device, so the
+        captured launches are valid for every replay."""
+        if generations % per_graph:
+            raise ValueError("generations must be a multiple of per_graph")
+        if self._graph is None or self._graph_steps != per_graph:
+            self.step_fused()                                # warm-up outside the capture (module load, attributes)
+            generations -= 1
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(per_graph):
+                    self.step_fused()
+            self._graph, self._graph_steps = g, per_graph
+            for _ in range(generations % per_graph):
+                self.step_fused()
+            generations -= generations % per_graph
+        for _ in range(generations // per_graph):
+            self._graph.replay()
 
     def poll(self):
         """(converged, generations, best energy) -- one small device-to-host read."""

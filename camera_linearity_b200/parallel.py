@@ -88,3 +88,70 @@ def allreduce_pair_sums(pair_acc: torch.Tensor) -> torch.Tensor:
     if world_size() > 1:
         dist.all_reduce(pair_acc, op=dist.ReduceOp.SUM)
     return pair_acc
+
+
+class PeerExchange:
+    """One peer-visible exchange buffer per rank for K4's fused tail kernel (``cl_icrf_energy_population``):
+    every rank allocates its buffer (``cl_peer_alloc``: cudaMalloc + CUDA IPC handle), the 64-byte handles are
+    all-gathered through the process group, and every rank maps the others' buffers on its own device
+    (``cl_peer_open``).  The kernels then exchange the (S x pairs x 2) pair sums with plain stores over NVLink
+    and a flag per rank -- torch.distributed only carried the handles."""
+
+    def __init__(self, nbytes: int):
+        import ctypes as C
+        from . import _lib
+        from ._lib import check
+        self.lib = _lib.load()
+        self.world, self.rank = world_size(), rank()
+        if self.world > _lib.CL_MAX_PEERS:
+            raise ValueError(f"at most {_lib.CL_MAX_PEERS} ranks")
+        own = C.c_void_p()
+        handle = _lib.IpcHandle()
+        check(self.lib.cl_peer_alloc(int(nbytes), C.byref(own), C.byref(handle)), "cl_peer_alloc")
+        self.own = own.value
+        self.ptrs = [None] * self.world
+        self.ptrs[self.rank] = self.own
+        self._opened = []
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.bytes))
+            for r, raw in enumerate(handles):
+                if r == self.rank:
+                    continue
+                h = _lib.IpcHandle()
+                C.memmove(C.byref(h), raw, 64)
+                ptr = C.c_void_p()
+                check(self.lib.cl_peer_open(C.byref(h), C.byref(ptr)), "cl_peer_open")
+                self.ptrs[r] = ptr.value
+                self._opened.append(ptr.value)
+            dist.barrier()                 # every buffer is mapped everywhere before the first kernel pushes
+
+    def peer_group(self):
+        from . import _lib
+        pg = _lib.PeerGroup()
+        pg.world, pg.rank = self.world, self.rank
+        for r, p in enumerate(self.ptrs):
+            pg.buffers[r] = p
+        return pg
+
+    def close(self):
+        if self.own is None:
+            return
+        if self.world > 1 and is_distributed():
+            torch.cuda.synchronize()
+            dist.barrier()                 # nobody unmaps while a peer's kernel may still push
+        for p in self._opened:
+            self.lib.cl_peer_close(p)
+        self._opened = []
+        self.lib.cl_peer_free(self.own)
+        self.own = None
+
+    def __del__(self):
+        try:
+            if self.own is not None:
+                for p in self._opened:
+                    self.lib.cl_peer_close(p)
+                self.lib.cl_peer_free(self.own)
+                self.own = None
+        except Exception:
+            pass

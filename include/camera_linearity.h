@@ -207,6 +207,37 @@ int cl_icrf_energy_partial(const cl_icrf_problem* p, const void* tables,
 int cl_icrf_energy_finalize(const cl_icrf_problem* p, const double* pair_acc,
                             const int32_t* valid, double* energy /* device [S] */, void* stream);
 
+/* The whole objective for one population on this rank's pixel shard in two launches -- the partial kernel and
+ * a fused tail: CTA reduction -> exchange of the (S x pairs x 2) sums with the other ranks through PEER MEMORY
+ * (plain stores into every peer's exchange buffer over NVLink + a flag; no NCCL launch) -> identical finalize
+ * on every rank.  Replaces the loop body of solve_channel (ICRF_calibration_exposure.py:357-370 calling
+ * _energy_function :148-201) for a population sharded over the GPUs of one node.
+ *   peers->buffers[r]: device pointer, valid on THIS device, to rank r's exchange buffer of
+ *   cl_icrf_exchange_bytes(p, world) bytes, zero-initialised once (cl_peer_alloc does that; buffers[rank] is
+ *   this rank's own).  world == 1: any zeroed device buffer of that size; nothing is exchanged.
+ *   Every rank must make the same sequence of calls (the buffers carry a generation counter).
+ *   pair_acc receives the sums over ALL ranks, energy the finalised energies. */
+#define CL_MAX_PEERS 16
+typedef struct cl_peer_group {
+    int32_t world, rank;
+    void* buffers[CL_MAX_PEERS];
+} cl_peer_group;
+size_t cl_icrf_exchange_bytes(const cl_icrf_problem* p, int world);
+int cl_icrf_energy_population(const cl_icrf_problem* p, const void* tables, const uint8_t* dn, const double* std,
+                              const double* exposure_s /* HOST [N] */, int64_t n_pixels, const int32_t* valid,
+                              double* pair_acc, double* energy, void* workspace, size_t workspace_bytes,
+                              const cl_peer_group* peers, void* stream);
+
+/* Peer-visible device buffers (CUDA IPC) for the exchange above: cl_peer_alloc on the owning rank (cudaMalloc,
+ * zero-filled, synchronous), the 64-byte handle travels to the other processes by any means
+ * (torch.distributed.all_gather_object in parallel.py), cl_peer_open maps it there.  These four calls are the
+ * only ones of the library that allocate or synchronise; they are set-up, not data path. */
+typedef struct cl_ipc_handle { unsigned char bytes[64]; } cl_ipc_handle;
+int cl_peer_alloc(size_t bytes, void** dev_ptr, cl_ipc_handle* handle);
+int cl_peer_open(const cl_ipc_handle* handle, void** dev_ptr);
+int cl_peer_close(void* dev_ptr);
+int cl_peer_free(void* dev_ptr);
+
 /* ---------------------------------------------------------------------------------------------
  * Linearity analysis of one exposure pair (first "next" row) -- replaces
  * AbstractMeasurand.apply_thresholds (modules/measurand.py:375-428), compute_difference
@@ -252,6 +283,13 @@ int cl_quantize_8bit(const double* val, int64_t n_samples, double max_dn, uint8_
 int cl_de_trial(const double* pop, int n_members, int n_params, double dither_lo, double dither_hi,
                 double crossover, uint64_t seed, const int64_t* generation, const double* lower,
                 const double* upper, double* trial, double* params, void* stream);
+/* cl_de_trial fused with cl_icrf_curves (one launch: CTA s draws member s's trial vector and builds its curve
+ * and tables).  n_members <= p->n_candidates; the padding candidates evaluate the zero parameter vector. */
+int cl_de_trial_curves(const cl_icrf_problem* p, const double* pop, int n_members, double dither_lo,
+                       double dither_hi, double crossover, uint64_t seed, const int64_t* generation,
+                       const double* lower, const double* upper, double* trial, double* params,
+                       const double* mean_icrf, const double* pca, double* curves, int32_t* valid, void* tables,
+                       void* stream);
 int cl_de_select(double* pop, double* energies, const double* trial, const double* trial_energies,
                  int n_members, int n_params, double tol, double atol, int64_t* generation, int32_t* status,
                  double* best, void* stream);

@@ -87,3 +87,34 @@ def test_device_driver_reaches_the_scipy_optimum():
     # same optimum from both drivers (the searches differ: scipy's Generator vs counter-based draws)
     assert abs(res["device"][2] - res["scipy"][2]) <= 0.05 * e_true + 1e-12
     assert res["device"][3] <= 400
+
+
+def test_fused_generation_and_cuda_graph_match_the_unfused_steps():
+    """cl_de_trial_curves + cl_icrf_energy_population + cl_de_select (4 launches, replayed from a CUDA graph) must
+    walk exactly the path of the unfused generation (cl_de_trial, cl_icrf_curves, partial, finalize, select)."""
+    from scipy.stats import qmc
+    mean, pca, p_true, curve, dn, t = _calibration_problem()
+    unit = torch.from_numpy(qmc.Sobol(d=5, seed=np.random.default_rng(9)).random(n=64)).cuda()
+    ev_a = cl.EnergyEvaluator(mean, pca, dn, None, 5, 250, True, t, 64, shard=False)
+    de_a = ops.DeviceDE(ev_a.device_energies, [-0.5] * 5, [0.5] * 5, unit, seed=9, tol=0.0)
+    ev_b = cl.EnergyEvaluator(mean, pca, dn, None, 5, 250, True, t, 64, shard=False)
+    de_b = ops.DeviceDE.for_plan(ev_b.plan, [-0.5] * 5, [0.5] * 5, unit, seed=9, tol=0.0)
+    assert torch.equal(de_a.pop, de_b.pop) and torch.equal(de_a.energies, de_b.energies)
+    for _ in range(24):
+        de_a.step()
+    de_b.run_graph(24, per_graph=8)
+    torch.cuda.synchronize()
+    assert torch.equal(de_a.pop, de_b.pop) and torch.equal(de_a.energies, de_b.energies)
+    assert de_a.poll()[1] == de_b.poll()[1] == 24
+    # and with uncertainty stacks, S not a multiple of 32 (padding candidates)
+    rng = np.random.default_rng(4)
+    sd = rng.uniform(0.002, 0.02, dn.shape)
+    unit40 = unit[:40].clone()
+    ev_c = cl.EnergyEvaluator(mean, pca, dn, sd, 5, 250, True, t, 40, shard=False)
+    de_c = ops.DeviceDE(ev_c.device_energies, [-0.5] * 5, [0.5] * 5, unit40, seed=3, tol=0.0)
+    ev_d = cl.EnergyEvaluator(mean, pca, dn, sd, 5, 250, True, t, 40, shard=False)
+    de_d = ops.DeviceDE.for_plan(ev_d.plan, [-0.5] * 5, [0.5] * 5, unit40, seed=3, tol=0.0)
+    for _ in range(9):
+        de_c.step()
+        de_d.step_fused()
+    assert torch.equal(de_c.pop, de_d.pop) and torch.equal(de_c.energies, de_d.energies)

@@ -59,6 +59,17 @@ def _worker(rank, world, port, n_dev, q):
     torch.cuda.synchronize()
     out["pop"] = de.pop.cpu().numpy()
     out["energies"] = de.energies.cpu().numpy()
+    out["exchange"] = ev.exchange
+    if ev.exchange == "peer":
+        # the fused generation replayed from a CUDA graph, pair sums pushed through peer memory: same walk
+        ev2 = cl.EnergyEvaluator(mean, pca, dn, None, 5, 250, True, t, 64, shard=True)
+        de2 = ops.DeviceDE.for_plan(ev2.plan, [-0.5] * 5, [0.5] * 5, torch.from_numpy(unit).to(dev), seed=7, tol=0.0)
+        de2.run_graph(12, per_graph=4)
+        torch.cuda.synchronize()
+        out["pop_graph"] = de2.pop.cpu().numpy()
+        # the NCCL route must give the same energies as the peer route
+        ev3 = cl.EnergyEvaluator(mean, pca, dn, std, 5, 250, True, t, params.shape[1], shard=True, exchange="nccl")
+        out["nccl_std"] = ev3(params)
     torch.distributed.barrier()
     q.put((rank, out))
     torch.distributed.destroy_process_group()
@@ -99,3 +110,8 @@ def test_k4_kernels_on_two_rank_shards_allreduce_and_finalize():
     assert out[0][1]["launches"] > 0 and out[1][1]["launches"] > 0                  # the CUDA kernels ran on both
     assert np.array_equal(out[0][1]["pop"], out[1][1]["pop"])
     assert np.array_equal(out[0][1]["energies"], out[1][1]["energies"])
+    assert out[0][1]["exchange"] == ("peer" if n_dev >= 2 else "nccl")
+    if n_dev >= 2:
+        assert np.array_equal(out[0][1]["pop_graph"], out[0][1]["pop"])
+        assert np.array_equal(out[0][1]["pop_graph"], out[1][1]["pop_graph"])
+        np.testing.assert_allclose(out[0][1]["nccl_std"], out[0][1][True], rtol=1e-13)
