@@ -466,6 +466,13 @@ def run_ours(args, wl):
             k4 = k4_block(dev, rank, world, cpu=not args.no_cpu)
         except Exception as exc:
             k4 = {"error": repr(exc)}
+    cfg5 = None
+    if not args.no_extra and CFG5["stacks"] % world == 0:
+        try:
+            cfg5 = {"f64_std": cfg5_measure(dev, rank, world, 2, 3),
+                    "std_table": cfg5_measure(dev, rank, world, 2, 3, std_table=True)}
+        except Exception as exc:
+            cfg5 = {"error": repr(exc)}
     extra = {}
     if rank == 0 and not args.no_extra:
         try:
@@ -516,9 +523,212 @@ def run_ours(args, wl):
                     "api": "as `e2e`, with ExposureSeries.process_HDR_image(STD_data=...) and no uncertainty images: only "
                            "the uint8 exposures cross PCIe"}},
         "k4_icrf_fit": k4,
+        "cfg5_sharded_batch": cfg5,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "extra": extra,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- cfg5: 64 stacks x 12 x 8K 16-bit
+CFG5 = dict(H=4320, W=7680, N=12, stacks=64, t0=0.0005, ratio=1.7,
+            label="cfg5: batch of 64 stacks x 12 exposures 7680x4320x1 uint16 + f64 std, 65536-row ICRF, sharded over the GPUs")
+
+
+def cfg5_tables(dev):
+    import torch
+    x16 = np.linspace(0, 1, 65536)
+    icrf = torch.from_numpy((x16 ** 2.1).reshape(-1, 1)).to(dev)
+    diff = torch.from_numpy(np.gradient(x16 ** 2.1, 2 / 65535).reshape(-1, 1)).to(dev)
+    stdlut = torch.from_numpy((0.002 + 0.02 * np.sqrt(x16)).reshape(-1, 1)).to(dev)
+    return icrf, diff, stdlut
+
+
+def cfg5_stack_device(seed, dev, with_std=True):
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    H, W, N = CFG5["H"], CFG5["W"], CFG5["N"]
+    t = [CFG5["t0"] * CFG5["ratio"] ** k for k in range(N)]
+    rad = torch.rand((H, W, 1), generator=g, device=dev, dtype=torch.float32) * 25
+    dn = [torch.round(65535 * torch.clamp(rad * tk, 0, 1) ** (1 / 2.2)).to(torch.int32).to(torch.uint16) for tk in t]
+    del rad
+    std = ([torch.rand((H, W, 1), generator=g, device=dev, dtype=torch.float64) * 0.018 + 0.002 for _ in t]
+           if with_std else None)
+    return dn, std, t
+
+
+def cfg5_measure(dev, rank, world, steps, warmup, std_table=False):
+    """The sharded batch of BASELINE config 5: 64 stacks split over the ranks (8 per GPU at N = 8), no collective.
+    Each rank keeps min(64 / world, 8) DISTINCT stacks resident (8 stacks = 36 GB) and merges its 64 / world stacks per
+    step by cycling over them, so every merge reads data far larger than L2.  Strong scaling: the batch is fixed."""
+    import torch
+    import torch.distributed as dist
+    from camera_linearity_b200 import ops
+    per_rank = CFG5["stacks"] // world
+    resident = min(per_rank, 8)
+    icrf, diff, stdlut = cfg5_tables(dev)
+    stacks = [cfg5_stack_device(5000 + 64 * rank + i, dev, with_std=not std_table) for i in range(resident)]
+    n = CFG5["H"] * CFG5["W"]
+    out = (torch.empty((CFG5["H"], CFG5["W"], 1), dtype=torch.float64, device=dev),
+           torch.empty((CFG5["H"], CFG5["W"], 1), dtype=torch.float64, device=dev))
+    kw = dict(std_lut=stdlut) if std_table else {}
+
+    def step():
+        for i in range(per_rank):
+            dn, std, t = stacks[i % resident]
+            ops.hdr_merge(dn, std, t, icrf, diff, out=out, **kw)
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tm = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_step = float(tm.item()) / steps
+    pix_exp = CFG5["stacks"] * n * CFG5["N"]
+    b_std = 0 if std_table else 8
+    alg_stack = CFG5["N"] * n * (2 + b_std) + n * 16
+    peak, _ = hbm_peak()
+    del stacks, out
+    torch.cuda.empty_cache()
+    return {"workload": CFG5["label"], "uncertainty": "STD table (65536 rows, fused into the ICRF gather)" if std_table
+            else "float64 uncertainty images", "value": pix_exp / (ms_step * 1e-3) / 1e9, "unit": "Gpix*exposures/s",
+            "scaling": "strong", "ms_per_step": ms_step, "stacks_per_rank_per_step": per_rank,
+            "distinct_resident_stacks_per_rank": resident, "ms_per_stack": ms_step / per_rank,
+            "algorithmic_bytes_per_stack": alg_stack,
+            "achieved_GB/s_per_gpu": alg_stack / (ms_step / per_rank) / 1e6,
+            "frac_of_hbm_peak": alg_stack / (ms_step / per_rank) / 1e6 / peak,
+            "bound": "L2 gather throughput: one divergent 16-byte (32-byte with the STD table) table gather per "
+                     "sample-exposure from a 1 MB (2 MB) table; tools/microbench/gather_bench.cu measures the chip's "
+                     "random-gather rate, see DESIGN.md"}
+
+
+def run_cfg5(args):
+    """`--workload cfg5`: the sharded 16-bit batch as the main line (device-resident value, e2e from pinned host
+    buffers, CPU port on a row crop)."""
+    import torch
+    import torch.distributed as dist
+    import camera_linearity_b200 as cl
+    from camera_linearity_b200 import _lib, ops, parallel
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    rank, world, local = parallel.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if CFG5["stacks"] % world:
+        raise SystemExit("cfg5 needs a GPU count that divides 64")
+    steps = max(1, min(args.steps, 5))
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    main_res = cfg5_measure(dev, rank, world, steps, max(3, args.warmup))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - launches0
+    tab_res = cfg5_measure(dev, rank, world, steps, 3, std_table=True)
+
+    # e2e: every stack of the rank's share is uploaded from pinned host memory (one pinned stack, re-sent: the
+    # bytes are real, a 255 GB batch does not fit host memory), merged through ExposureSeries.process_HDR_image and
+    # read back
+    per_rank = CFG5["stacks"] // world
+    icrf, diff, stdlut = cfg5_tables(dev)
+    dn, std, t = cfg5_stack_device(777 + rank, dev)
+    host_dn = [x.cpu().pin_memory() for x in dn]
+    host_std = [x.cpu().pin_memory() for x in std]
+    del dn, std
+    torch.cuda.empty_cache()
+    cl.GlobalSettings.configure(BIT_DEPTH=16)
+    shape = (CFG5["H"], CFG5["W"], 1)
+    outs = [(torch.empty(shape, dtype=torch.float64).pin_memory(), torch.empty(shape, dtype=torch.float64).pin_memory())
+            for _ in range(2)]
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    feats = lambda tk: {"illumination": "bf", "magnification": "10x", "exposure": tk, "subject": "s"}
+
+    def e2e_stack(i):
+        with torch.cuda.stream(streams[i % 2]):
+            sets = []
+            for k in range(CFG5["N"]):
+                s_ = cl.ImageSet(features=feats(t[k]), measurand=cl.Measurand(None, host_std[k].to(dev, non_blocking=True)))
+                s_.set_digital_numbers(host_dn[k])
+                sets.append(s_)
+            series = cl.ExposureSeries(input_image_sets=sets)
+            series.process_HDR_image(icrf, diff, dark_list=[], flat_list=[])
+            m = series.merged_image_set.measurand
+            outs[i % 2][0].copy_(m.val, non_blocking=True)
+            outs[i % 2][1].copy_(m.std, non_blocking=True)
+
+    e2e_stacks = min(per_rank, 8)                      # a bounded share of the step, scaled to the whole step below
+    for i in range(2):
+        e2e_stack(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_stacks):
+        e2e_stack(i)
+    for st in streams:
+        st.synchronize()
+    if world > 1:
+        dist.barrier()
+    tm = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    n = CFG5["H"] * CFG5["W"]
+    e2e_value = world * e2e_stacks * n * CFG5["N"] / (float(tm.item()) * 1e-3) / 1e9
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import hdr_merge as om
+        rows = 24
+        rng = np.random.default_rng(5)
+        tt = np.array(t)
+        rad = rng.uniform(0, 1, (rows, CFG5["W"], 1)) * 25
+        dn_h = [np.rint(65535 * np.clip(rad * tk, 0, 1) ** (1 / 2.2)).astype(np.uint16) for tk in tt]
+        std_h = [rng.uniform(0.002, 0.02, (rows, CFG5["W"], 1)) for _ in tt]
+        x16 = np.linspace(0, 1, 65536)
+        t0 = time.perf_counter()
+        om.hdr_merge(dn_h, std_h, tt, x16 ** 2.1, np.gradient(x16 ** 2.1, 2 / 65535), max_dn=65535)
+        dt = time.perf_counter() - t0
+        cpu = {"value": rows * CFG5["W"] * CFG5["N"] / dt / 1e9, "unit": "Gpix*exposures/s", "cores": 1, "kind": "port",
+               "sample": f"oracle (NumPy port) on a {rows}-row crop of one stack ({rows}x{CFG5['W']}x1 uint16, 12 exposures), {dt:.2f} s"}
+    peak, peak_src = hbm_peak()
+    line = {
+        "metric": "HDR merge throughput", "value": main_res["value"], "unit": "Gpix*exposures/s", "n_gpus": world,
+        "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": CFG5["label"], "stacks_per_rank_per_step": main_res["stacks_per_rank_per_step"],
+                   "distinct_resident_stacks_per_rank": main_res["distinct_resident_stacks_per_rank"],
+                   "l2": "each merge streams 4.5 GB (8 distinct resident stacks per rank = 36 GB) vs 126 MB L2",
+                   "parallelism": f"64 independent stacks over {world} GPU(s), no collective"},
+        "roofline": {"bound": "hbm", "achieved": main_res["achieved_GB/s_per_gpu"], "peak": peak, "unit": "GB/s",
+                     "frac": main_res["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                     "kernel": "merge_wide_kernel<12,false> (+ build_wide_table_kernel, 1 MB)",
+                     "algorithmic_bytes_per_launch": main_res["algorithmic_bytes_per_stack"], "note": main_res["bound"]},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "Gpix*exposures/s", "h2d_bytes_per_step": CFG5["stacks"] * CFG5["N"] * n * 10,
+                "d2h_bytes_per_step": CFG5["stacks"] * n * 16, "ms_per_step": float(tm.item()) / e2e_stacks * per_rank,
+                "stacks_timed_per_rank": e2e_stacks,
+                "api": "ExposureSeries.process_HDR_image per stack from pinned host tensors (uint16 exposures + float64 "
+                       "uncertainty images uploaded, float64 result read back, two alternating streams); timed on "
+                       f"{e2e_stacks} of the rank's {per_rank} stacks per step and scaled"},
+        "std_table_variant": tab_res,
+        "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line))
 
@@ -643,28 +853,6 @@ def extra_kernels(dev):
         out[name] = {"ms": ms, "GB/s": nb / ms / 1e6, "frac_of_hbm_peak": nb / ms / 1e6 / peak,
                      "Gpix*exposures/s": wl["H"] * wl["W"] * wl["N"] / ms / 1e6, "algorithmic_bytes": nb}
         del data, o
-    # K2 on one stack of cfg5 (12 exposures 4320x7680x1 uint16, 65536-row ICRF), with f64 std
-    # images (fused-table kernel, algo 3) and with the STD table instead (generic kernel, 2 B/sample-exposure)
-    H5, W5, N5 = 4320, 7680, 12
-    x16 = np.linspace(0, 1, 65536)
-    icrf16 = torch.from_numpy((x16 ** 2.1).reshape(-1, 1)).to(dev)
-    diff16 = torch.from_numpy(np.gradient(x16 ** 2.1, 2 / 65535).reshape(-1, 1)).to(dev)
-    stdlut16 = torch.from_numpy((0.002 + 0.02 * np.sqrt(x16)).reshape(-1, 1)).to(dev)
-    rad = torch.rand((H5, W5, 1), generator=g, device=dev, dtype=torch.float32) * 25
-    t5 = [0.0005 * 1.7 ** k for k in range(N5)]
-    dn5 = [torch.round(65535 * torch.clamp(rad * tk, 0, 1) ** (1 / 2.2)).to(torch.int32).to(torch.uint16) for tk in t5]
-    del rad
-    std5 = [torch.rand((H5, W5, 1), generator=g, device=dev, dtype=torch.float64) * 0.018 + 0.002 for _ in t5]
-    o5 = (torch.empty((H5, W5, 1), dtype=torch.float64, device=dev), torch.empty((H5, W5, 1), dtype=torch.float64, device=dev))
-    n5 = H5 * W5
-    for name, kw, nb in (("k2_cfg5_one_stack_16bit", dict(std=std5), N5 * n5 * 10 + n5 * 16),
-                         ("k2_cfg5_one_stack_16bit_std_table", dict(std=None, std_lut=stdlut16), N5 * n5 * 2 + n5 * 16)):
-        std_arg = kw.pop("std")
-        ms = timed(lambda: ops.hdr_merge(dn5, std_arg, t5, icrf16, diff16, out=o5, **kw), reps=5, warm=2)
-        out[name] = {"ms": ms, "GB/s": nb / ms / 1e6, "frac_of_hbm_peak": nb / ms / 1e6 / peak,
-                     "Gpix*exposures/s": n5 * N5 / ms / 1e6, "algorithmic_bytes": nb,
-                     "shape": "12 exposures 4320x7680x1 uint16, 65536-row ICRF"}
-    del dn5, std5, o5
     # K1: linearize one 4K RGB frame with std (25 B/sample)
     dn = torch.randint(0, 256, (2160, 3840, 3), generator=g, device=dev, dtype=torch.uint8)
     sd = torch.rand((2160, 3840, 3), generator=g, device=dev, dtype=torch.float64) * 0.02
@@ -713,12 +901,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg5"])
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 generic kernel, 2 staged kernel")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    if args.workload == "cfg5" and args.impl == "ours":
+        return run_cfg5(args)
+    wl = WORKLOADS[args.workload if args.workload in WORKLOADS else "cfg2"]
     if args.impl == "reference":
         run_reference_arm(args, args.workload)
     else:

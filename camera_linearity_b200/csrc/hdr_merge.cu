@@ -599,7 +599,11 @@ extern "C" {
 size_t cl_hdr_merge_workspace_bytes(const cl_hdr_merge_args* a) {
     if (!a) return 0;
     size_t bytes = 0;
-    if (a->bits > 256) bytes += cl::table_bytes(a->bits, a->channels);   // (the fused-table kernel needs less)
+    if (a->bits > 256) {                 // generic tables, or the 16-bit kernel's (32-byte rows with an STD table)
+        const size_t generic = cl::table_bytes(a->bits, a->channels);
+        const size_t wide = cl::wide_table_bytes(a->bits, a->channels, a->std_lut != nullptr);
+        bytes += generic > wide ? generic : wide;
+    }
     // bad-pixel work list of the staged kernel (uint8, 3 channels, dark frames present)
     bool any_dark = false;
     if (a->dark)
@@ -675,7 +679,7 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
     // 16-bit stacks with uncertainty images and N <= 16: fused-table kernel (hdr_merge_wide.cu)
     bool wide = false;
     if (!tab_smem && a->algo != 1 && a->algo != 2) {
-        if (workspace && aligned(workspace, 16) && workspace_bytes >= wide_table_bytes(p.bits, p.C))
+        if (workspace && aligned(workspace, 32) && workspace_bytes >= wide_table_bytes(p.bits, p.C, !all_std))
             p.g_tab32 = reinterpret_cast<const double2*>(workspace);
         wide = merge_wide_supported(p, a->dn_bytes, all_std);
         if (a->algo == 3 && !wide) return p.g_tab32 ? CL_ERR_UNSUPPORTED : CL_ERR_WORKSPACE;

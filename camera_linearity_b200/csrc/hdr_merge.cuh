@@ -225,7 +225,7 @@ int launch_merge_staged_lut(const MergeParams& p, cudaStream_t stream);   // hdr
 bool merge_staged_lut_supported(const MergeParams& p);
 int launch_merge_wide(const MergeParams& p, cudaStream_t stream);     // hdr_merge_wide.cu
 bool merge_wide_supported(const MergeParams& p, int dn_bytes, bool all_std_images);
-size_t wide_table_bytes(int bits, int C);
+size_t wide_table_bytes(int bits, int C, bool with_std_lut);
 bool merge_staged_supported(const MergeParams& p, bool all_std_images);
 // hdr_merge.cu
 int launch_merge_generic_range(const MergeParams& p, int64_t first_item, cudaStream_t stream);
