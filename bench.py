@@ -857,15 +857,17 @@ def extra_kernels(dev):
     dn = torch.randint(0, 256, (2160, 3840, 3), generator=g, device=dev, dtype=torch.uint8)
     sd = torch.rand((2160, 3840, 3), generator=g, device=dev, dtype=torch.float64) * 0.02
     ms = timed(lambda: ops.linearize(dn, sd, icrf, diff))
-    out["k1_linearize"] = {"ms": ms, "GB/s": dn.numel() * 25 / ms / 1e6, "shape": "2160x3840x3 u8 + f64 std"}
+    out["k1_linearize"] = {"ms": ms, "GB/s": dn.numel() * 25 / ms / 1e6, "frac_of_hbm_peak": dn.numel() * 25 / ms / 1e6 / peak,
+                           "shape": "2160x3840x3 u8 + f64 std"}
     del dn, sd
-    # linearity analysis of one exposure pair (next row 8f-1): 2160x3840x3 float64 val+std, two passes of 32 B/sample
+    # linearity analysis of one exposure pair (next row 8f-1): 2160x3840x3 float64 val+std, one pass of 32 B/sample
     xv = torch.rand((2160, 3840, 3), generator=g, device=dev, dtype=torch.float64) + 0.05
     yv = torch.rand((2160, 3840, 3), generator=g, device=dev, dtype=torch.float64) + 0.05
     xs = torch.rand((2160, 3840, 3), generator=g, device=dev, dtype=torch.float64) * 0.02 + 0.001
     ys = torch.rand((2160, 3840, 3), generator=g, device=dev, dtype=torch.float64) * 0.02 + 0.001
     ms = timed(lambda: ops.pair_statistics(xv, xs, yv, ys, 0.5, [0.1] * 3, [0.9] * 3))
-    out["pair_statistics"] = {"ms": ms, "GB/s": xv.numel() * 64 / ms / 1e6, "shape": "one exposure pair 2160x3840x3 f64 val+std"}
+    out["pair_statistics"] = {"ms": ms, "GB/s": xv.numel() * 32 / ms / 1e6, "frac_of_hbm_peak": xv.numel() * 32 / ms / 1e6 / peak,
+                              "shape": "one exposure pair 2160x3840x3 f64 val+std, every input read once (32 B/sample)"}
     del xv, yv, xs, ys
     # K3: cfg4, 600 frames 1080x1920x3
     base = torch.randint(20, 231, (1, 1080, 1920, 3), generator=g, device=dev, dtype=torch.int16)
@@ -877,10 +879,12 @@ def extra_kernels(dev):
     ws = torch.empty(ops._lib.load().cl_welford_stack_workspace_bytes(600, frames[0].numel()), dtype=torch.uint8, device=dev)
     ms = timed(lambda: ops.welford_stack(frames, None, 255.0, ws), reps=3, warm=1)
     nb = frames.numel() + frames[0].numel() * 17
-    out["k3_welford_stack"] = {"ms": ms, "GB/s": nb / ms / 1e6, "Gpix*frames/s": 600 * 1080 * 1920 / ms / 1e6,
+    out["k3_welford_stack"] = {"ms": ms, "GB/s": nb / ms / 1e6, "frac_of_hbm_peak": nb / ms / 1e6 / peak,
+                               "Gpix*frames/s": 600 * 1080 * 1920 / ms / 1e6,
                                "shape": "cfg4: 600x1080x1920x3 u8"}
     ms = timed(lambda: ops.welford_stack(frames, icrf, 255.0, ws), reps=3, warm=1)       # linearised frames (ICRF given)
-    out["k3_welford_stack_icrf"] = {"ms": ms, "GB/s": nb / ms / 1e6, "shape": "cfg4 with ICRF[frame, c] as the sample value"}
+    out["k3_welford_stack_icrf"] = {"ms": ms, "GB/s": nb / ms / 1e6, "frac_of_hbm_peak": nb / ms / 1e6 / peak,
+                                    "shape": "cfg4 with ICRF[frame, c] as the sample value"}
     # the reference's Welford recurrence (oracle port of video_processing.py:183-217) on a bounded number of frames
     from oracle import welford as ow
     n_f = 12

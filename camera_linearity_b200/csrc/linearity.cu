@@ -4,23 +4,29 @@
 // compute_dimension_statistics(axis=(0,1)) (:318-350) as ExposureSeries.process_linearity chains
 // them (exposure_series.py:421-446): the reference materialises the absolute and relative
 // difference images with their uncertainties (4 full float64 images per pair) and then reduces
-// them; here two streaming passes over the four inputs (32 B/sample each) produce the 6 x C numbers.
+// them; here ONE streaming pass over the four inputs (32 B/sample) produces the 6 x C numbers.
 //
-// Pass 1 accumulates, per channel and for the absolute and the relative difference,
+// Per channel and for the absolute and the relative difference the pass accumulates
 //   weighted:   sum(w), sum(v*w) with w = 1/sigma   (np.nansum semantics: NaN terms are skipped
 //               individually), sum(sigma), count(sigma) for the mean uncertainty;
-//   unweighted: count, sum(v).
-// Pass 2 accumulates sum(w*(v-mean)^2) (or sum((v-mean)^2)).  Block partials are combined in a fixed
-// order (deterministic); the reference's pairwise summation differs at the 1e-13 level.
+//   unweighted: count, sum(v);
+//   and, for the variance sum(w*(v-mean)^2), the SHIFTED moments T0 = sum(w), T1 = sum(w*d), T2 = sum(w*d^2)
+//   with d = v - K over the samples the variance counts:  sum(w*(v-mean)^2) = T2 - 2(mean-K) T1 + (mean-K)^2 T0.
+// K (per channel, abs and rel) is the plain mean of the first few thousand samples -- every block derives it
+// from the same L2-hot chunk in the same order, so it is one number and costs no launch; with K within a few
+// standard errors of the mean the expansion loses nothing (round 1 made a second pass over the inputs, 64 B
+// per sample, only to centre the variance).  Block partials are combined in a fixed order (deterministic); the
+// reference's pairwise summation differs at the 1e-13 level.
 #include "common.cuh"
 
 namespace cl {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kBlocks = 444;  // 148 SMs x 3 resident CTAs; fixed (not sm_count) so the summation order is machine-independent
-constexpr int kQ1 = 8;    // pass-1 quantities per channel: {sw, svw, ssig, nsig} x {abs, rel}
-constexpr int kQ2 = 2;    // pass-2 quantities per channel: {abs, rel}
+constexpr int kBlocks = 296;  // 148 SMs x 2 resident CTAs; fixed (not sm_count) so the summation order is machine-independent
+constexpr int kQ1 = 8;    // sums per channel: {sw, svw, ssig, nsig} x {abs, rel}
+constexpr int kQ = 14;    // + the shifted moments {T0, T1, T2} x {abs, rel}
+constexpr int kShiftSamples = 16;   // per thread: the provisional mean K comes from the first 16 * lanes_used samples
 
 struct PairArgs {
     const double* x_val;
@@ -111,19 +117,21 @@ __device__ __forceinline__ void accumulate1(double (&acc)[8], const Diff& d) {
     }
 }
 
+// shifted moments of the variance set (the samples round 1's second pass counted)
 template <bool USE_STD>
-__device__ __forceinline__ void accumulate2(double (&acc)[2], const Diff& d, double ma, double mr) {
-    const double da = __dsub_rn(d.a, ma), dr = __dsub_rn(d.r, mr);
-    double ta = __dmul_rn(da, da), tr = __dmul_rn(dr, dr);
+__device__ __forceinline__ void accumulate_shifted(double (&acc)[kQ], const Diff& d, double ka, double kr) {
+    const double da = __dsub_rn(d.a, ka), dr = __dsub_rn(d.r, kr);
+    double wa = 1.0, wr = 1.0;
     bool bad_a = d.bad_v, bad_r = d.bad_v;
     if (USE_STD) {
-        ta = __dmul_rn(d.wa, ta);                                      // weights * (values - mean)**2
-        tr = __dmul_rn(d.wr, tr);
+        wa = d.wa;
+        wr = d.wr;
         bad_a = bad_a || d.bad_sa;
         bad_r = d.bad_sr;
     }
-    if (!bad_a && not_nan(ta)) acc[0] += ta;
-    if (!bad_r && not_nan(tr)) acc[1] += tr;
+    const double ta = __dmul_rn(wa, __dmul_rn(da, da)), tr = __dmul_rn(wr, __dmul_rn(dr, dr));
+    if (!bad_a && not_nan(ta)) { acc[8] += wa; acc[9] = fma(wa, da, acc[9]); acc[10] += ta; }
+    if (!bad_r && not_nan(tr)) { acc[11] += wr; acc[12] = fma(wr, dr, acc[12]); acc[13] += tr; }
 }
 
 // Deterministic block reduction of per-thread accumulators: thread t owns channel (t % C) because
@@ -144,27 +152,77 @@ __device__ __forceinline__ void block_reduce(const double (&acc)[Q], int C, int 
     __syncthreads();
 }
 
+__device__ __forceinline__ double ka_of(const double (&shift)[4][CL_MAX_CHANNELS], int c) {
+    return shift[1][c] > 0.0 ? shift[0][c] / shift[1][c] : 0.0;
+}
+__device__ __forceinline__ double kr_of(const double (&shift)[4][CL_MAX_CHANNELS], int c) {
+    return shift[3][c] > 0.0 ? shift[2][c] / shift[3][c] : 0.0;
+}
+
 template <bool USE_STD>
-__global__ void __launch_bounds__(kThreads, 3)
-pair_pass1_kernel(const PairArgs p, double* __restrict__ partial /* [blocks][kQ1][C] */) {
+__global__ void __launch_bounds__(kThreads, 2)
+pair_stats_kernel(const PairArgs p, double* __restrict__ partial /* [blocks][kQ][C] */) {
     const int C = p.C;
     const int lanes_used = (kThreads / C) * C;               // threads beyond that idle: keeps t % C fixed
     const int64_t stride = (int64_t)gridDim.x * lanes_used;
-    double acc[kQ1] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if ((int)threadIdx.x < lanes_used) {
-        const int c = threadIdx.x % C;                       // (block offset and stride are multiples of C)
-        const double lo = p.lower[c], hi = p.upper[c];
+    __shared__ double shift[4][CL_MAX_CHANNELS];             // {sum a, count a, sum r, count r} -> K
+    double acc[kQ];
+#pragma unroll
+    for (int q = 0; q < kQ; ++q) acc[q] = 0.0;
+    const bool active = (int)threadIdx.x < lanes_used;
+    const int c = threadIdx.x % C;                           // (block offset and stride are multiples of C)
+    const double lo = p.lower[c], hi = p.upper[c];
+    // ---- provisional means K from the first kShiftSamples * lanes_used samples (identical in every block) ----
+    {
+        double pa[4] = {0, 0, 0, 0};
+        if (active) {
+            for (int u = 0; u < kShiftSamples; ++u) {
+                const int64_t i = (int64_t)u * lanes_used + threadIdx.x;
+                if (i >= p.n) break;
+                const Diff d = difference(p, load_raw(p, i), lo, hi, false);
+                const bool fa = !d.bad_v && fabs(d.a) < __longlong_as_double(0x7ff0000000000000LL);
+                const bool fr = !d.bad_v && fabs(d.r) < __longlong_as_double(0x7ff0000000000000LL);
+                if (fa) { pa[0] += d.a; pa[1] += 1.0; }
+                if (fr) { pa[2] += d.r; pa[3] += 1.0; }
+            }
+        }
+        __shared__ double sh4[4][kThreads];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sh4[q][threadIdx.x] = pa[q];
+        __syncthreads();
+        if (threadIdx.x < 4 * C) {
+            const int q = threadIdx.x / C, cc = threadIdx.x % C;
+            double t = 0.0;
+            for (int l = cc; l < lanes_used; l += C) t += sh4[q][l];
+            shift[q][cc] = t;
+        }
+        __syncthreads();
+    }
+    const double ka = ka_of(shift, c), kr = kr_of(shift, c);
+    if (active) {
         int64_t i = (int64_t)blockIdx.x * lanes_used + threadIdx.x;
         for (; i + (kUnroll - 1) * stride < p.n; i += kUnroll * stride) {
             Raw raw[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) raw[u] = load_raw(p, i + u * stride);
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) accumulate1<USE_STD>(acc, difference(p, raw[u], lo, hi, USE_STD));
+            for (int u = 0; u < kUnroll; ++u) {
+                const Diff d = difference(p, raw[u], lo, hi, USE_STD);
+                double (&a8)[8] = reinterpret_cast<double (&)[8]>(acc);
+                accumulate1<USE_STD>(a8, d);
+                accumulate_shifted<USE_STD>(acc, d, ka, kr);
+            }
         }
-        for (; i < p.n; i += stride) accumulate1<USE_STD>(acc, difference(p, load_raw(p, i), lo, hi, USE_STD));
+        for (; i < p.n; i += stride) {
+            const Diff d = difference(p, load_raw(p, i), lo, hi, USE_STD);
+            double (&a8)[8] = reinterpret_cast<double (&)[8]>(acc);
+            accumulate1<USE_STD>(a8, d);
+            accumulate_shifted<USE_STD>(acc, d, ka, kr);
+        }
     }
-    block_reduce<kQ1>(acc, C, lanes_used, partial + (int64_t)blockIdx.x * kQ1 * C);
+    block_reduce<kQ>(acc, C, lanes_used, partial + (int64_t)blockIdx.x * kQ * C);
+    if (blockIdx.x == 0 && threadIdx.x < 2 * C)              // the shifts, for the final kernel
+        partial[(int64_t)gridDim.x * kQ * C + threadIdx.x] = threadIdx.x < C ? ka_of(shift, threadIdx.x) : kr_of(shift, threadIdx.x - C);
 }
 
 // Fixed-order sum of one column of the per-block partials by one warp: lanes stride over the blocks, then
@@ -177,58 +235,30 @@ __device__ __forceinline__ double column_sum(const double* __restrict__ partial,
     return warp_sum(s);
 }
 
-// means[q][c]: q = 0 abs mean, 1 rel mean (+ the pass-1 totals kept for the final kernel); one warp per total
-__global__ void pair_means_kernel(const double* __restrict__ partial, int n_blocks, int C,
-                                  double* __restrict__ totals /* [kQ1][C] */, double* __restrict__ means /* [2][C] */) {
+// stats[which][k][c]: which 0 = absolute, 1 = relative; k 0 = mean, 1 = std, 2 = error.  One block: a warp per
+// column total, then one thread per (which, c).
+__global__ void pair_final_kernel(const double* __restrict__ partial, int n_blocks, int C, int use_std,
+                                  double* __restrict__ stats) {
+    __shared__ double totals[kQ * CL_MAX_CHANNELS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int o = warp; o < kQ1 * C; o += (int)(blockDim.x >> 5)) {
-        const double s = column_sum(partial, n_blocks, kQ1 * C, o);
+    for (int o = warp; o < kQ * C; o += (int)(blockDim.x >> 5)) {
+        const double s = column_sum(partial, n_blocks, kQ * C, o);
         if (lane == 0) totals[o] = s;
     }
     __syncthreads();
     const int t = threadIdx.x;
-    if (t < 2 * C) {
-        const int which = t / C, c = t % C;                  // 0 = abs, 1 = rel
-        means[t] = totals[(which * 4 + 1) * C + c] / totals[(which * 4 + 0) * C + c];
-    }
-}
-
-template <bool USE_STD>
-__global__ void __launch_bounds__(kThreads, 3)
-pair_pass2_kernel(const PairArgs p, const double* __restrict__ means, double* __restrict__ partial /* [blocks][kQ2][C] */) {
-    const int C = p.C;
-    const int lanes_used = (kThreads / C) * C;
-    const int64_t stride = (int64_t)gridDim.x * lanes_used;
-    double acc[kQ2] = {0, 0};
-    if ((int)threadIdx.x < lanes_used) {
-        const int c = threadIdx.x % C;
-        const double ma = means[c], mr = means[C + c];
-        const double lo = p.lower[c], hi = p.upper[c];
-        int64_t i = (int64_t)blockIdx.x * lanes_used + threadIdx.x;
-        for (; i + (kUnroll - 1) * stride < p.n; i += kUnroll * stride) {
-            Raw raw[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) raw[u] = load_raw(p, i + u * stride);
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) accumulate2<USE_STD>(acc, difference(p, raw[u], lo, hi, USE_STD), ma, mr);
-        }
-        for (; i < p.n; i += stride) accumulate2<USE_STD>(acc, difference(p, load_raw(p, i), lo, hi, USE_STD), ma, mr);
-    }
-    block_reduce<kQ2>(acc, C, lanes_used, partial + (int64_t)blockIdx.x * kQ2 * C);
-}
-
-// stats[which][k][c]: which 0 = absolute, 1 = relative; k 0 = mean, 1 = std, 2 = error; one warp per (which, c)
-__global__ void pair_final_kernel(const double* __restrict__ partial2, int n_blocks, int C, int use_std,
-                                  const double* __restrict__ totals, const double* __restrict__ means,
-                                  double* __restrict__ stats) {
-    const int t = threadIdx.x >> 5;
     if (t >= 2 * C) return;
     const int which = t / C, c = t % C;
-    const double s = column_sum(partial2, n_blocks, kQ2 * C, t);
-    if ((threadIdx.x & 31) != 0) return;
+    const double K = partial[(int64_t)n_blocks * kQ * C + t];
     const double denom = totals[(which * 4 + 0) * C + c];                     // sum of weights / count
-    stats[(which * 3 + 0) * C + c] = means[t];
-    stats[(which * 3 + 1) * C + c] = sqrt(s / denom);
+    const double mean = totals[(which * 4 + 1) * C + c] / denom;
+    const double T0 = totals[(8 + which * 3 + 0) * C + c], T1 = totals[(8 + which * 3 + 1) * C + c],
+                 T2 = totals[(8 + which * 3 + 2) * C + c];
+    const double dm = mean - K;
+    double q = fma(dm * dm, T0, fma(-2.0 * dm, T1, T2));                      // sum w (v - mean)^2
+    if (q < 0.0) q = 0.0;
+    stats[(which * 3 + 0) * C + c] = mean;
+    stats[(which * 3 + 1) * C + c] = sqrt(q / denom);
     stats[(which * 3 + 2) * C + c] = use_std ? totals[(which * 4 + 2) * C + c] / totals[(which * 4 + 3) * C + c]
                                              : __longlong_as_double(0x7ff8000000000000LL);
 }
@@ -240,7 +270,7 @@ extern "C" {
 
 size_t cl_pair_statistics_workspace_bytes(int channels) {
     const size_t c = channels > 0 ? channels : 1;
-    return ((size_t)cl::kBlocks * (cl::kQ1 + cl::kQ2) * c + cl::kQ1 * c + 2 * c) * sizeof(double);
+    return ((size_t)cl::kBlocks * cl::kQ * c + 2 * c) * sizeof(double);     // block partials + the two shifts per channel
 }
 
 int cl_pair_statistics(const double* x_val, const double* x_std, const double* y_val, const double* y_std,
@@ -262,20 +292,12 @@ int cl_pair_statistics(const double* x_val, const double* x_std, const double* y
     }
     const bool use_std = x_std != nullptr || y_std != nullptr;
     cudaStream_t s = (cudaStream_t)stream;
-    double* partial1 = reinterpret_cast<double*>(workspace);
-    double* partial2 = partial1 + (size_t)kBlocks * kQ1 * channels;
-    double* totals = partial2 + (size_t)kBlocks * kQ2 * channels;
-    double* means = totals + (size_t)kQ1 * channels;
-    if (use_std) pair_pass1_kernel<true><<<kBlocks, kThreads, 0, s>>>(p, partial1);
-    else pair_pass1_kernel<false><<<kBlocks, kThreads, 0, s>>>(p, partial1);
+    double* partial = reinterpret_cast<double*>(workspace);
+    if (use_std) pair_stats_kernel<true><<<kBlocks, kThreads, 0, s>>>(p, partial);
+    else pair_stats_kernel<false><<<kBlocks, kThreads, 0, s>>>(p, partial);
     int st = launched();
     if (st != CL_OK) return st;
-    pair_means_kernel<<<1, 1024, 0, s>>>(partial1, kBlocks, channels, totals, means);
-    if ((st = launched()) != CL_OK) return st;
-    if (use_std) pair_pass2_kernel<true><<<kBlocks, kThreads, 0, s>>>(p, means, partial2);
-    else pair_pass2_kernel<false><<<kBlocks, kThreads, 0, s>>>(p, means, partial2);
-    if ((st = launched()) != CL_OK) return st;
-    pair_final_kernel<<<1, 32 * 2 * CL_MAX_CHANNELS, 0, s>>>(partial2, kBlocks, channels, use_std ? 1 : 0, totals, means, stats);
+    pair_final_kernel<<<1, 1024, 0, s>>>(partial, kBlocks, channels, use_std ? 1 : 0, stats);
     return launched();
 }
 

@@ -39,6 +39,38 @@ def _require_cuda(*tensors: Optional[Tensor]) -> torch.device:
     return dev
 
 
+def _first_cuda_device(obj) -> Optional[torch.device]:
+    if isinstance(obj, torch.Tensor):
+        return obj.device if obj.is_cuda else None
+    if isinstance(obj, (list, tuple)):
+        for item in obj:
+            dev = _first_cuda_device(item)
+            if dev is not None:
+                return dev
+    return None
+
+
+def _on_device(fn):
+    """Run an operator with the device of its tensors current: the library launches on the CURRENT device and on
+    ``torch.cuda.current_stream()``, so tensors living on cuda:N while another device is current would otherwise be
+    handed to the wrong device's stream (and the per-device queries -- SM count, occupancy, function attributes --
+    would describe the wrong GPU)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            dev = _first_cuda_device(a)
+            if dev is not None:
+                break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -80,6 +112,7 @@ def _lut_pair(icrf: Tensor, icrf_diff: Optional[Tensor], channels: int):
 
 
 # ------------------------------------------------------------------------------------- K1
+@_on_device
 def linearize(val: Tensor, std: Optional[Tensor], icrf: Tensor, icrf_diff: Optional[Tensor] = None,
               max_dn: float = 255.0, return_bins: bool = False):
     """``out[..., c] = ICRF[bin(val[..., c]), c]`` (+ ``ICRF_diff[bin] * std``); K1 of DESIGN.md.
@@ -122,6 +155,7 @@ def linearize(val: Tensor, std: Optional[Tensor], icrf: Tensor, icrf_diff: Optio
 
 
 # ------------------------------------------------------------------------------------- K2
+@_on_device
 def flat_roi_means(flat: Tensor, flat_std: Tensor, roi: Tuple[int, int, int, int],
                    max_dn: float = 255.0) -> Tensor:
     """ROI means ``[m_0..m_{C-1}, ms_0..ms_{C-1}]`` of a flat field (measurand.py:561-583)."""
@@ -144,6 +178,7 @@ def flat_roi_means(flat: Tensor, flat_std: Tensor, roi: Tuple[int, int, int, int
     return out
 
 
+@_on_device
 def hdr_merge(dn: Sequence[Tensor], std: Optional[Sequence[Optional[Tensor]]],
               exposures: Sequence[float], icrf: Tensor, icrf_diff: Tensor, *,
               std_lut: Optional[Tensor] = None,
@@ -264,6 +299,7 @@ def hdr_merge(dn: Sequence[Tensor], std: Optional[Sequence[Optional[Tensor]]],
     return out_val, out_std
 
 
+@_on_device
 def gaussian_weight(val: Tensor) -> Tuple[Tensor, Tensor]:
     """``apply_gaussian_weight`` (measurand.py:606-618): returns (w, dw)."""
     _require_cuda(val)
@@ -275,6 +311,7 @@ def gaussian_weight(val: Tensor) -> Tuple[Tensor, Tensor]:
     return w, dw
 
 
+@_on_device
 def bad_pixel_filter(val: Tensor, std: Optional[Tensor], dark_val: Tensor, threshold: float,
                      kernel: int) -> Tuple[Tensor, Optional[Tensor]]:
     """``filter_larger_than_by_map`` (measurand.py:543-557) on float64 (H, W, C) images."""
@@ -293,6 +330,7 @@ def bad_pixel_filter(val: Tensor, std: Optional[Tensor], dark_val: Tensor, thres
     return out_v, out_s
 
 
+@_on_device
 def flat_field_normalize(val: Tensor, std: Tensor, flat_val: Tensor, flat_std: Tensor,
                          flat_means: Tensor) -> Tuple[Tensor, Tensor]:
     """``normalize_by_map`` (measurand.py:559-604) given the ROI means."""
@@ -307,6 +345,7 @@ def flat_field_normalize(val: Tensor, std: Tensor, flat_val: Tensor, flat_std: T
 
 
 # ------------------------------------------------------------------------------------- K3
+@_on_device
 def welford_update(frames: Tensor, mean: Tensor, m2: Tensor, count0: int,
                    icrf: Optional[Tensor] = None, max_dn: float = 255.0) -> int:
     """Fold ``frames`` (F, H, W, C) uint8 into the running (mean, m2) state in place -- the
@@ -330,6 +369,7 @@ def welford_update(frames: Tensor, mean: Tensor, m2: Tensor, count0: int,
     return count0 + f
 
 
+@_on_device
 def welford_finalize(mean: Tensor, m2: Optional[Tensor], count: int, max_dn: float = 255.0):
     """Returns (sem float64 or None, mean_u8) -- video_processing.py:210-215 with repair R9."""
     _require_cuda(mean, m2)
@@ -342,6 +382,7 @@ def welford_finalize(mean: Tensor, m2: Optional[Tensor], count: int, max_dn: flo
     return sem, mean_u8
 
 
+@_on_device
 def welford_stack(frames: Tensor, icrf: Optional[Tensor] = None, max_dn: float = 255.0,
                   workspace: Optional[Tensor] = None):
     """Mean / SEM / uint8 mean of a resident frame stack (F, H, W, C) uint8 (K3 of DESIGN.md)."""
@@ -372,6 +413,20 @@ def welford_stack(frames: Tensor, icrf: Optional[Tensor] = None, max_dn: float =
 
 
 # ------------------------------------------------------------------------------------- K4
+def _plan_device(fn):
+    """Method flavour of ``_on_device`` for objects that carry ``self.device``."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        dev = self.device
+        if dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 class IcrfEnergyPlan:
     """Device-resident state of one calibration problem (one colour channel): pixel samples,
     PCA basis, scratch.  ``partial()`` and ``finalize()`` map onto the C ABI calls so that a
@@ -380,6 +435,7 @@ class IcrfEnergyPlan:
     def __init__(self, dn_stack: Tensor, std_stack: Optional[Tensor], exposures, mean_icrf,
                  pca_basis: Tensor, lower: int, upper: int, use_mean_icrf: bool, n_candidates: int):
         dev = _require_cuda(dn_stack, std_stack, pca_basis)
+        self.device = dev
         self.lib = _lib.load()
         if dn_stack.dtype != torch.uint8:
             raise TypeError("the calibration value stack must be uint8 "
@@ -443,22 +499,26 @@ class IcrfEnergyPlan:
             raise ValueError(f"params must be ({self.n_real}, {self.prob.n_params})")
         self.params[: self.n_real].copy_(p, non_blocking=True)
 
+    @_plan_device
     def curves_and_tables(self) -> None:
         check(self.lib.cl_icrf_curves(C.byref(self.prob), _ptr(self.mean), _ptr(self.pca), _ptr(self.params),
                                       _ptr(self.curves), _ptr(self.valid), _ptr(self.tables), _stream()),
               "cl_icrf_curves")
 
+    @_plan_device
     def partial(self) -> Tensor:
         check(self.lib.cl_icrf_energy_partial(C.byref(self.prob), _ptr(self.tables), _ptr(self.dn), _ptr(self.std),
                                               self.exposures, self.n_pixels, _ptr(self.pair_acc), _ptr(self.ws),
                                               self.ws_bytes, _stream()), "cl_icrf_energy_partial")
         return self.pair_acc
 
+    @_plan_device
     def finalize(self) -> Tensor:
         check(self.lib.cl_icrf_energy_finalize(C.byref(self.prob), _ptr(self.pair_acc), _ptr(self.valid),
                                                _ptr(self.energy), _stream()), "cl_icrf_energy_finalize")
         return self.energy[: self.n_real]
 
+    @_plan_device
     def population(self) -> Tensor:
         """Partial kernel + fused tail (CTA reduction, exchange with the attached peers, finalize): the energies
         of the candidates whose curves / tables are current, over the pixels of ALL ranks."""
@@ -486,6 +546,7 @@ class DeviceDE:
     def __init__(self, evaluate, lower, upper, init_unit_population: Tensor, seed: int, dither=(0.0, 1.95),
                  recombination: float = 0.4, tol: float = 0.01, atol: float = 0.0):
         dev = _require_cuda(init_unit_population)
+        self.device = dev
         self.lib = _lib.load()
         self.evaluate = evaluate
         self.pop = _f64c(init_unit_population).clone()
@@ -509,6 +570,7 @@ class DeviceDE:
     def scaled(self, unit: Tensor) -> Tensor:
         return 0.5 * (self.lower + self.upper) + (unit - 0.5) * torch.abs(self.upper - self.lower)
 
+    @_plan_device
     def step(self) -> None:
         check(self.lib.cl_de_trial(_ptr(self.pop), self.S, self.P, float(self.dither[0]), float(self.dither[1]), self.cr,
                                    self.seed, _ptr(self.generation), _ptr(self.lower), _ptr(self.upper),
@@ -532,6 +594,7 @@ class DeviceDE:
         self._graph_steps = 0
         return self
 
+    @_plan_device
     def step_fused(self) -> None:
         plan = self.plan
         check(self.lib.cl_de_trial_curves(C.byref(plan.prob), _ptr(self.pop), self.S, float(self.dither[0]),
@@ -576,6 +639,7 @@ class DeviceDE:
 
 
 # ------------------------------------------------------------------------------------- linearity
+@_on_device
 def pair_statistics(x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor, y_std: Optional[Tensor],
                     multiplier: float, lower: Optional[Sequence[Optional[float]]] = None,
                     upper: Optional[Sequence[Optional[float]]] = None) -> Tensor:
@@ -605,6 +669,7 @@ def pair_statistics(x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor, y_std
 
 
 # ------------------------------------------------------------------------------------- histogram
+@_on_device
 def channel_histogram(val: Tensor, std: Optional[Tensor], channel: int, bins: int, included_range=None):
     """np.histogram of the finite values of one channel (measurand.py:430-469), weighted by 1/std when
     ``std`` is given.  Returns ``(hist, bin_edges)`` as NumPy arrays like np.histogram; only the ``bins``
@@ -642,6 +707,7 @@ def channel_histogram(val: Tensor, std: Optional[Tensor], channel: int, bins: in
 
 
 # ------------------------------------------------------------------------------------- egress
+@_on_device
 def quantize_8bit(val: Tensor, max_dn: float = 255.0, return_max: bool = False):
     """The array part of ImageSet.save_8bit (image_set.py:343-350): normalise by ``amax`` when it exceeds 1,
     scale by MAX_DN, round half-even, cast to uint8 -- on the device, so the result crosses PCIe as one
@@ -661,7 +727,18 @@ def quantize_8bit(val: Tensor, max_dn: float = 255.0, return_max: bool = False):
 
 
 # ------------------------------------------------------------------------------------- custom ops
-# Registered for discoverability / composability with torch.library; they call the functions above.
+# The C-ABI layer as PyTorch custom ops (``torch.ops.camera_linearity.*``): functional, tensor-in / tensor-out
+# wrappers over the functions above, one per entry point of include/camera_linearity.h that does data-path work.
+# Optional per-exposure images travel as a list plus an index list (-1 = none): torch schemas have no
+# Optional-in-list for custom ops.
+def _pick(images: List[Tensor], index: Sequence[int], n: int) -> Optional[List[Optional[Tensor]]]:
+    if not images:
+        return None
+    if len(index) != n:
+        raise ValueError("index list must have one entry per exposure")
+    return [None if int(i) < 0 else images[int(i)] for i in index]
+
+
 @torch.library.custom_op("camera_linearity::linearize", mutates_args=(), device_types="cuda")
 def _op_linearize(val: Tensor, std: Optional[Tensor], icrf: Tensor, icrf_diff: Optional[Tensor],
                   max_dn: float) -> List[Tensor]:
@@ -676,11 +753,122 @@ def _op_hdr_merge(dn: List[Tensor], std: List[Tensor], exposures: List[float], i
     return [v, s]
 
 
+@torch.library.custom_op("camera_linearity::hdr_merge_corrected", mutates_args=(), device_types="cuda")
+def _op_hdr_merge_corrected(dn: List[Tensor], std: List[Tensor], std_index: List[int], std_lut: Optional[Tensor],
+                            exposures: List[float], icrf: Tensor, icrf_diff: Tensor, darks: List[Tensor],
+                            dark_index: List[int], dark_scales: List[float], dark_threshold: float,
+                            median_kernel: int, flat: Optional[Tensor], flat_std: Optional[Tensor],
+                            flat_means: Optional[Tensor], algo: int) -> List[Tensor]:
+    """cl_hdr_merge with everything it takes: ``std[std_index[k]]`` is exposure k's uncertainty image (-1: sigma from
+    ``std_lut``), ``darks[dark_index[k]]`` its dark frame (-1: none), ``dark_scales[k]`` the exposure scaling of that
+    dark frame, the flat field with its ROI means (``flat_roi_means``)."""
+    n = len(dn)
+    v, s = hdr_merge(dn, _pick(std, std_index, n), exposures, icrf, icrf_diff, std_lut=std_lut,
+                     darks=_pick(darks, dark_index, n), dark_scales=dark_scales if dark_scales else None,
+                     dark_threshold=dark_threshold, median_kernel=median_kernel, flat=flat, flat_std=flat_std,
+                     flat_means=flat_means, algo=algo)
+    return [v, s]
+
+
+@torch.library.custom_op("camera_linearity::flat_roi_means", mutates_args=(), device_types="cuda")
+def _op_flat_roi_means(flat: Tensor, flat_std: Tensor, roi: List[int], max_dn: float) -> Tensor:
+    return flat_roi_means(flat, flat_std, tuple(roi), max_dn)
+
+
 @torch.library.custom_op("camera_linearity::welford_stack", mutates_args=(), device_types="cuda")
 def _op_welford_stack(frames: Tensor, icrf: Optional[Tensor], max_dn: float) -> List[Tensor]:
     return list(welford_stack(frames, icrf, max_dn))
 
 
+@torch.library.custom_op("camera_linearity::welford_update", mutates_args=("mean", "m2"), device_types="cuda")
+def _op_welford_update(frames: Tensor, mean: Tensor, m2: Tensor, count0: int, icrf: Optional[Tensor],
+                       max_dn: float) -> None:
+    welford_update(frames, mean, m2, count0, icrf, max_dn)
+
+
+@torch.library.custom_op("camera_linearity::welford_finalize", mutates_args=(), device_types="cuda")
+def _op_welford_finalize(mean: Tensor, m2: Tensor, count: int, max_dn: float) -> List[Tensor]:
+    sem, mean_u8 = welford_finalize(mean, m2, count, max_dn)
+    return [sem, mean_u8]
+
+
 @torch.library.custom_op("camera_linearity::gaussian_weight", mutates_args=(), device_types="cuda")
 def _op_gaussian_weight(val: Tensor) -> List[Tensor]:
     return list(gaussian_weight(val))
+
+
+def _icrf_problem(n_candidates: int, n_params: int, datapoints: int, use_mean: bool, lower: int, upper: int,
+                  n_exposures: int, use_std: bool) -> IcrfProblem:
+    if n_candidates % 32:
+        raise ValueError("candidates must be padded to a multiple of 32 (one lane per candidate)")
+    return IcrfProblem(int(n_candidates), int(n_params), int(datapoints), 1 if use_mean else 0, int(lower), int(upper),
+                       int(n_exposures), 1 if use_std else 0)
+
+
+@torch.library.custom_op("camera_linearity::icrf_energy_curves", mutates_args=(), device_types="cuda")
+def _op_icrf_energy_curves(params: Tensor, mean_icrf: Optional[Tensor], pca: Tensor, lower: int, upper: int,
+                           n_exposures: int, use_std: bool) -> List[Tensor]:
+    """cl_icrf_curves: (S, n_params) candidates -> [curves (S, D) float64, valid (S,) int32, tables (uint8 scratch
+    consumed by icrf_energy_partial)].  S must be a multiple of 32."""
+    _require_cuda(params, mean_icrf, pca)
+    lib = _lib.load()
+    prm, pc = _f64c(params), _f64c(pca)
+    s_, n_params = (int(v) for v in prm.shape)
+    d_ = int(pc.shape[0])
+    prob = _icrf_problem(s_, n_params, d_, mean_icrf is not None, lower, upper, n_exposures, use_std)
+    curves = torch.empty((s_, d_), dtype=torch.float64, device=prm.device)
+    valid = torch.empty(s_, dtype=torch.int32, device=prm.device)
+    tables = torch.empty(lib.cl_icrf_tables_bytes(C.byref(prob)), dtype=torch.uint8, device=prm.device)
+    mean = None if mean_icrf is None else _f64c(mean_icrf)
+    check(lib.cl_icrf_curves(C.byref(prob), _ptr(mean), _ptr(pc), _ptr(prm), _ptr(curves), _ptr(valid), _ptr(tables),
+                             _stream()), "cl_icrf_curves")
+    return [curves, valid, tables]
+
+
+@torch.library.custom_op("camera_linearity::icrf_energy_partial", mutates_args=(), device_types="cuda")
+def _op_icrf_energy_partial(tables: Tensor, dn: Tensor, std: Optional[Tensor], exposures: List[float],
+                            n_candidates: int, n_params: int, datapoints: int, use_mean: bool, lower: int,
+                            upper: int) -> Tensor:
+    """cl_icrf_energy_partial: per-(candidate, exposure pair) numerator / denominator sums over the given pixels,
+    (S, pairs, 2) float64 -- what ranks all-reduce before icrf_energy_finalize."""
+    _require_cuda(tables, dn, std)
+    lib = _lib.load()
+    if dn.dtype != torch.uint8 or dn.ndim != 2:
+        raise TypeError("dn must be a (pixels, N) uint8 tensor")
+    n_px, n_exp = (int(v) for v in dn.shape)
+    prob = _icrf_problem(n_candidates, n_params, datapoints, use_mean, lower, upper, n_exp, std is not None)
+    sd = None if std is None else _f64c(std)
+    acc = torch.empty((n_candidates, n_exp * (n_exp - 1) // 2, 2), dtype=torch.float64, device=dn.device)
+    ws_bytes = lib.cl_icrf_energy_workspace_bytes(C.byref(prob), n_px)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dn.device)
+    t = (C.c_double * n_exp)(*[float(x) for x in exposures])
+    check(lib.cl_icrf_energy_partial(C.byref(prob), _ptr(tables), _ptr(dn.contiguous()), _ptr(sd), t, n_px, _ptr(acc),
+                                     _ptr(ws), ws_bytes, _stream()), "cl_icrf_energy_partial")
+    return acc
+
+
+@torch.library.custom_op("camera_linearity::icrf_energy_finalize", mutates_args=(), device_types="cuda")
+def _op_icrf_energy_finalize(pair_acc: Tensor, valid: Tensor, n_exposures: int) -> Tensor:
+    """cl_icrf_energy_finalize: nanmean over the pairs of num / den, gated or NaN -> +inf."""
+    _require_cuda(pair_acc, valid)
+    lib = _lib.load()
+    s_ = int(pair_acc.shape[0])
+    prob = _icrf_problem(s_, 1, 2, True, 0, 1, n_exposures, False)
+    energy = torch.empty(s_, dtype=torch.float64, device=pair_acc.device)
+    check(lib.cl_icrf_energy_finalize(C.byref(prob), _ptr(_f64c(pair_acc)), _ptr(valid.contiguous()), _ptr(energy),
+                                      _stream()), "cl_icrf_energy_finalize")
+    return energy
+
+
+@torch.library.custom_op("camera_linearity::pair_statistics", mutates_args=(), device_types="cuda")
+def _op_pair_statistics(x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor, y_std: Optional[Tensor],
+                        multiplier: float, lower: List[float], upper: List[float]) -> Tensor:
+    """cl_pair_statistics; empty ``lower`` / ``upper`` = no thresholds."""
+    return pair_statistics(x_val, x_std, y_val, y_std, multiplier, list(lower) if lower else None,
+                           list(upper) if upper else None)
+
+
+@torch.library.custom_op("camera_linearity::quantize_8bit", mutates_args=(), device_types="cuda")
+def _op_quantize_8bit(val: Tensor, max_dn: float) -> List[Tensor]:
+    out, mx = quantize_8bit(val, max_dn, return_max=True)
+    return [out, mx]
