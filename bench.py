@@ -348,7 +348,6 @@ def run_ours(args, wl):
     kernel_events = [step() for _ in range(args.steps)]
     stop.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0
     total_ms = start.elapsed_time(stop)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
@@ -460,6 +459,7 @@ def run_ours(args, wl):
     e2e_tab_value = world * pix_exp * n_e2e / (e2e_tab_ms * 1e-3) / 1e9
     h2d_tab = wl["N"] * n_samp
     del host, dark_sets, flats, data
+    clocks = sampler.stop() if rank == 0 else None      # sampled through the timed steps, the STD-table loop and both e2e arms
     k4 = None
     if not args.no_extra:
         try:
@@ -800,6 +800,18 @@ def k4_block(dev, rank, world, cpu=True):
             gen_ms = timed(de.step, reps=40, warm=3)
             res["de_generation"] = {"ms": gen_ms, "evals/s": 64e3 / gen_ms, "generations/s": 1e3 / gen_ms,
                                     "how": "generic step with an NCCL all-reduce between partial and finalize"}
+        if world > 1 and ev.exchange == "peer":
+            # the same objective with the pair sums all-reduced by NCCL between the partial and finalize launches
+            # (round 1's path): what the peer-memory tail replaces
+            ev_n = cl.EnergyEvaluator(mean, pca, stack, sdv, 5, 250, True, tt, 64, shard=True, exchange="nccl")
+            ms_n = timed(lambda: ev_n.device_energies(p_dev), reps=50)
+            de_n = ops.DeviceDE(ev_n.device_energies, [-0.5] * 5, [0.5] * 5, torch.from_numpy(unit).to(dev), seed=7, tol=0.0)
+            gen_n = timed(de_n.step, reps=40, warm=3)
+            res["nccl_allreduce_variant"] = {"ms_per_population": ms_n, "evals/s": 64e3 / ms_n,
+                                             "de_generation_ms": gen_n, "de_evals/s": 64e3 / gen_n,
+                                             "how": "curves, partial, reduce, ncclAllReduce(S x pairs x 2 f64), finalize "
+                                                    "(+ de_trial, de_select): 7 launches per generation, host driven"}
+            del ev_n, de_n
         out[name] = res
         del ev, de
     if cpu and rank == 0:

@@ -133,7 +133,7 @@ def test_operators_follow_the_device_of_their_tensors():
     img = rng.integers(0, 256, (32, 40, 3), dtype=np.uint8)
     other = torch.device("cuda", 1)
     assert torch.cuda.current_device() == 0
-    v, _ = K.linearize(torch.from_numpy(img).to(other), None, torch.from_numpy(icrf).to(other), None, 255.0)
+    (v,) = K.linearize(torch.from_numpy(img).to(other), None, torch.from_numpy(icrf).to(other), None, 255.0)
     assert v.device == other
     ev, _ = ol.linearize(img, None, icrf, None)
     assert np.array_equal(v.cpu().numpy(), ev)

@@ -21,9 +21,19 @@ for path in sys.argv[1:]:
             g = r.get("de_generation", {})
             print(f"   k4 {name}: {r['ms_per_population']:.4f} ms/pop = {r['evals/s']:.0f} evals/s ({r['exchange']}); "
                   f"DE generation {g.get('ms', float('nan')):.4f} ms = {g.get('evals/s', float('nan')):.0f} evals/s"
-                  + (f"; cpu {r['cpu_baseline']['value']:.2f} evals/s" if 'cpu_baseline' in r else ""))
+                  + (f"; cpu {r['cpu_baseline']['value']:.2f} evals/s" if 'cpu_baseline' in r else "")
+                  + (f"; NCCL variant {r['nccl_allreduce_variant']['ms_per_population']:.4f} ms/pop, DE "
+                     f"{r['nccl_allreduce_variant']['de_generation_ms']:.4f} ms" if 'nccl_allreduce_variant' in r else ""))
     if "error" in k4:
         print("   k4 error:", k4["error"])
+    c5 = d.get("cfg5_sharded_batch") or {}
+    for name in ("f64_std", "std_table"):
+        if name in c5:
+            r = c5[name]
+            print(f"   cfg5 {name}: {r['value']:.1f} Gpix*exp/s, {r['ms_per_stack']:.3f} ms/stack, frac {r['frac_of_hbm_peak']:.3f}, "
+                  f"{r['stacks_per_rank_per_step']} stacks/rank/step")
+    if "error" in c5:
+        print("   cfg5 error:", c5["error"])
     for k, v in (d.get("extra") or {}).items():
         if isinstance(v, dict):
             print("   ", k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items() if a not in ("shape", "cpu_baseline")})
