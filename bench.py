@@ -272,7 +272,7 @@ class ClockSampler:
 def measured_traffic(workload):
     """DRAM bytes (read + write) of one cl_hdr_merge call -- the merge kernel plus the dark scan / patch
     / fix-up kernels it launches -- from the committed ncu capture."""
-    path = ROOT / "profiles" / "r01_traffic.json"
+    path = ROOT / "profiles" / "r02_traffic.json"
     try:
         entry = json.loads(path.read_text())[workload]
         return entry["dram_bytes_read"] + entry["dram_bytes_write"] + sum(entry.get("other_kernels", {}).values())
@@ -498,7 +498,7 @@ def run_ours(args, wl):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(args.workload) if args.algo != 1 else None, "traffic_source":
                      "ncu dram__bytes_read+write summed over the kernels of one cl_hdr_merge call (merge_staged 4.21 GB + "
-                     "dark scan / flat ROI / fix-up 0.18 GB), profiles/r01_traffic.json", "peak_source": peak_src, "kernel": ("one step = cl_flat_roi_means + cl_hdr_merge (dark_scan + merge_staged_kernel<16>, ~95% of the time, + merge_fixup); "
+                     "dark scan / flat ROI / fix-up 0.18 GB), profiles/r02_traffic.json", "peak_source": peak_src, "kernel": ("one step = cl_flat_roi_means + cl_hdr_merge (dark_scan + merge_staged_kernel<16>, ~95% of the time, + merge_fixup); "
                                 "achieved = algorithmic bytes / ms_per_step" if args.algo != 1 else "merge_generic_kernel"),
                      "algorithmic_bytes_per_launch": alg_bytes, "step_ms_by_per_step_events": kernel_ms},
         "cpu_baseline": cpu,

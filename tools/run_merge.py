@@ -1,6 +1,6 @@
 """Run ops.hdr_merge on the cfg2 bench stack a few times (profiling target for ncu).
 
-    python tools/run_merge.py [dark_threshold] [reps] [darks:0|1] [flat:0|1]
+    python tools/run_merge.py [dark_threshold] [reps] [darks:0|1] [flat:0|1] [lut]      (lut: sigma from the STD table)
 """
 import sys
 from pathlib import Path
@@ -19,6 +19,7 @@ def main():
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     use_darks = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
     use_flat = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
+    use_lut = len(sys.argv) > 5 and sys.argv[5] == "lut"
     dev = torch.device("cuda:0")
     wl = bench.WORKLOADS["cfg2"]
     data = bench.make_stack_device(wl, 1234, dev)
@@ -34,7 +35,9 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
     ev[0].record()
     for r in range(reps):
-        out = ops.hdr_merge(data["dn"], data["std"], t, icrf, diff, darks=data["darks"], dark_threshold=thr,
+        out = ops.hdr_merge(data["dn"], None if use_lut else data["std"], t, icrf, diff,
+                            std_lut=torch.from_numpy(bench.std_table(3)).to(dev) if use_lut else None,
+                            darks=data["darks"], dark_threshold=thr,
                             median_kernel=bench.KERNEL, flat=data["flat"], flat_std=data["flat_std"],
                             flat_means=means)
         ev[r + 1].record()
