@@ -752,7 +752,7 @@ def k4_block(dev, rank, world, cpu=True):
     """ICRF-fit loss evaluations per second on cfg3 with the pixels sharded over the `world` GPUs (collective: every
     rank calls it).  `population`: candidate curves + partial kernel + fused tail (CTA reduction, pair sums exchanged
     through peer memory, finalize) timed with CUDA events, max over ranks.  `de_generation`: the same inside the
-    device-resident DE (4 launches per generation, 8 generations per CUDA-graph replay)."""
+    device-resident DE (3 launches per generation, 8 generations per CUDA-graph replay)."""
     import torch
     import torch.distributed as dist
     import camera_linearity_b200 as cl
@@ -794,7 +794,7 @@ def k4_block(dev, rank, world, cpu=True):
             de.run_graph(8, per_graph=8)
             gen_ms = timed(lambda: de.run_graph(8, per_graph=8), reps=12, warm=2) / 8
             res["de_generation"] = {"ms": gen_ms, "evals/s": 64e3 / gen_ms, "generations/s": 1e3 / gen_ms,
-                                    "how": "cl_de_trial_curves + partial + fused tail + cl_de_select, CUDA graph of 8 generations"}
+                                    "how": "cl_de_trial_curves + partial + fused tail (reduce / exchange / finalize / DE selection), CUDA graph of 8 generations"}
         else:
             de = ops.DeviceDE(ev.device_energies, [-0.5] * 5, [0.5] * 5, torch.from_numpy(unit).to(dev), seed=7, tol=0.0)
             gen_ms = timed(de.step, reps=40, warm=3)

@@ -11,12 +11,12 @@ from .measurand import AbstractMeasurand, NumpyMeasurand, MeasurandFactory, meas
 from .image_set import ImageSet
 from .exposure_series import ExposureSeries, ExposurePair
 from . import general_functions, ops, parallel, video_processing, ICRF_calibration_exposure
-from .video_processing import welford_algorithm, welford_stack
+from .video_processing import compute_noise_profiles, welford_algorithm, welford_stack
 from .ICRF_calibration_exposure import _energy_function, EnergyEvaluator, calibration
 
 # `Measurand(val, std, use_cupy=...)` is both the reference's factory call and the class
 Measurand = _MeasurandClass
 
 __all__ = ["GlobalSettings", "Measurand", "AbstractMeasurand", "NumpyMeasurand", "MeasurandFactory", "measurand_to_numpy", "measurand_to_cupy",
-           "ImageSet", "ExposureSeries", "ExposurePair", "welford_algorithm", "welford_stack",
+           "ImageSet", "ExposureSeries", "ExposurePair", "welford_algorithm", "welford_stack", "compute_noise_profiles",
            "_energy_function", "EnergyEvaluator", "calibration", "ops", "parallel"]

@@ -59,6 +59,13 @@ class PeerGroup(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("buffers", C.c_void_p * CL_MAX_PEERS)]
 
 
+class DeSelectArgs(C.Structure):
+    """``cl_de_select_args`` (include/camera_linearity.h)."""
+    _fields_ = [("pop", C.c_void_p), ("energies", C.c_void_p), ("trial", C.c_void_p), ("n_members", C.c_int32),
+                ("n_params", C.c_int32), ("tol", C.c_double), ("atol", C.c_double), ("generation", C.c_void_p),
+                ("status", C.c_void_p), ("best", C.c_void_p)]
+
+
 class IpcHandle(C.Structure):
     """``cl_ipc_handle`` (include/camera_linearity.h)."""
     _fields_ = [("bytes", C.c_ubyte * 64)]
@@ -92,13 +99,17 @@ SIGNATURES = {
     "cl_icrf_energy_finalize": (_i, [C.POINTER(IcrfProblem), _vp, _vp, _vp, _vp]),
     "cl_icrf_exchange_bytes": (_sz, [C.POINTER(IcrfProblem), _i]),
     "cl_icrf_energy_population": (_i, [C.POINTER(IcrfProblem), _vp, _vp, _vp, C.POINTER(C.c_double), _i64, _vp, _vp,
-                                       _vp, _vp, _sz, C.POINTER(PeerGroup), _vp]),
+                                       _vp, _vp, _sz, C.POINTER(PeerGroup), C.POINTER(DeSelectArgs), _vp]),
     "cl_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p), C.POINTER(IpcHandle)]),
     "cl_peer_open": (_i, [C.POINTER(IpcHandle), C.POINTER(C.c_void_p)]),
     "cl_peer_close": (_i, [_vp]),
     "cl_peer_free": (_i, [_vp]),
     "cl_de_trial_curves": (_i, [C.POINTER(IcrfProblem), _vp, _i, _d, _d, _d, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _vp, _vp, _vp, _vp]),
+    "cl_measurand_binary": (_i, [_i, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "cl_measurand_log": (_i, [_i, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "cl_measurand_difference": (_i, [_vp, _vp, _vp, _vp, _d, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "cl_noise_profiles": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp]),
     "cl_channel_histogram": (_i, [_vp, _vp, _i64, _i, _i, _i, _d, _d, _vp, _vp, _vp]),
     "cl_de_trial": (_i, [_vp, _i, _i, _d, _d, _d, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cl_de_select": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp]),

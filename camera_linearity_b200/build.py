@@ -75,11 +75,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, _sources()))
-    r = subprocess.run([nvcc, "-shared", "-o", str(LIB), *map(str, objs),
+    tmp = OBJ_DIR / (LIB.name + ".tmp")             # link next to the objects, then move into place atomically
+    r = subprocess.run([nvcc, "-shared", "-o", str(tmp), *map(str, objs),
                         "-gencode", "arch=compute_100a,code=sm_100a"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     STAMP.write_text(_fingerprint())
     return LIB
 

@@ -56,5 +56,72 @@ __device__ __forceinline__ void trial_component(const double* __restrict__ pop, 
     param = __dadd_rn(__dmul_rn(0.5, __dadd_rn(lo[j], hi[j])), __dmul_rn(__dsub_rn(v, 0.5), fabs(__dsub_rn(hi[j], lo[j]))));
 }
 
+// One block (any size): selection, promotion of the best member to row 0, convergence test, generation counter.
+// Shared by de_select_kernel (de.cu) and the last block of K4's tail kernel (icrf_energy.cu).
+// status: [0] converged (0/1), [1] generations done, [2] members replaced this generation, [3] index the best
+// member came from;  best[0] = lowest energy, best[1] = std(E), best[2] = mean(E)
+__device__ __forceinline__ void select_block(double* __restrict__ pop, double* __restrict__ energies,
+                                             const double* __restrict__ trial, const double* trial_energies, int S,
+                                             int P, double tol, double atol, int64_t* __restrict__ generation,
+                                             int32_t* __restrict__ status, double* __restrict__ best) {
+    __shared__ int n_replaced;
+    __shared__ int best_idx;
+    if (threadIdx.x == 0) n_replaced = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        const double te = trial_energies[i];
+        if (te <= energies[i]) {                           // scipy _accept_trial: '<=' (a plateau keeps moving); NaN never replaces
+            energies[i] = te;
+            for (int j = 0; j < P; ++j) pop[i * P + j] = trial[i * P + j];
+            atomicAdd(&n_replaced, 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // np.argmin: first index of the minimum (NaN energies cannot occur: K4 maps NaN to +inf)
+        int l = 0;
+        double m = energies[0];
+        bool any_inf = false;
+        double sum = 0.0;
+        for (int i = 0; i < S; ++i) {
+            const double e = energies[i];
+            if (e < m) { m = e; l = i; }
+            any_inf = any_inf || isinf(e);
+            sum += e;
+        }
+        const double mean = sum / (double)S;
+        double ss = 0.0;
+        for (int i = 0; i < S; ++i) {
+            const double d = energies[i] - mean;
+            ss += d * d;
+        }
+        const double sd = sqrt(ss / (double)S);            // np.std: population standard deviation
+        best_idx = l;
+        status[0] = (!any_inf && sd <= atol + tol * fabs(mean)) ? 1 : 0;
+        generation[0] += 1;
+        status[1] = (int32_t)generation[0];
+        status[2] = n_replaced;
+        status[3] = l;
+        best[0] = m;
+        best[1] = sd;
+        best[2] = mean;
+    }
+    __syncthreads();
+    const int l = best_idx;                                // _promote_lowest_energy: swap rows 0 and l
+    if (l != 0) {
+        for (int j = threadIdx.x; j < P; j += blockDim.x) {
+            const double a = pop[j], b = pop[l * P + j];
+            pop[j] = b;
+            pop[l * P + j] = a;
+        }
+        if (threadIdx.x == 0) {
+            const double a = energies[0];
+            energies[0] = energies[l];
+            energies[l] = a;
+        }
+    }
+}
+
+
 }  // namespace de
 }  // namespace cl

@@ -258,21 +258,11 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             const double r0 = 1.0 / S0, r1 = 1.0 / S1, r2 = 1.0 / S2;
 
             // ---- pass B: one ring stage per exposure ----
-            // The phase check of the NEXT stage is issued before the arithmetic of the current one: an mbarrier
-            // try_wait takes ~90 cycles even when the phase has long completed, and with four consumer warps per
-            // scheduler that latency was exposed 17 times per tile.
             double av0 = 0.0, av1 = 0.0, av2 = 0.0, as0 = 0.0, as1 = 0.0, as2 = 0.0;
-            bool landed = mbar_try_wait(&c_full[s], phase);
 #pragma unroll
             for (int k = 0; k < NMAX; ++k) {
                 if (k < p.n) {
-                    if (!landed) mbar_wait(&c_full[s], phase);
-                    {
-                        int sn = s + 1;
-                        uint32_t pn = phase;
-                        if (sn == stages) { sn = 0; pn ^= 1; }
-                        landed = (k + 1 < p.n || has_flat) ? mbar_try_wait(&c_full[sn], pn) : false;
-                    }
+                    mbar_wait(&c_full[s], phase);
                     const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
                     const double g0 = sp[0], g1 = sp[1], g2 = sp[2];
                     const uint32_t q = pk[k];
@@ -295,7 +285,7 @@ merge_staged_kernel(const __grid_constant__ MergeParams p, const StagedLayout L,
             double u0, u1, u2;
             const int64_t i0 = px * kC;
             if (has_flat) {
-                if (!landed) mbar_wait(&c_full[s], phase);
+                mbar_wait(&c_full[s], phase);
                 const double* sp = reinterpret_cast<const double*>(ring + (size_t)s * kStdChunk) + tid * kC;
                 const double f0 = sp[0], f1 = sp[1], f2 = sp[2];
                 double rf0, rf1, rf2;

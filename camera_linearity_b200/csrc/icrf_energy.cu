@@ -477,6 +477,18 @@ struct PeerGroup {
     unsigned char* buf[CL_MAX_PEERS];
 };
 
+// optional DE selection run by the last block right after the finalize (cl_de_select fused in): pop == nullptr: none
+struct SelectArgs {
+    double* pop;
+    double* energies;
+    const double* trial;
+    int32_t n_members, n_params;
+    double tol, atol;
+    int64_t* generation;
+    int32_t* status;
+    double* best;
+};
+
 __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
     uint64_t v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -486,7 +498,7 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
 __global__ void __launch_bounds__(kTailThreads, 1)
 energy_tail_kernel(const double* __restrict__ cta_partial, int n_ctas, int S, int P, const int32_t* __restrict__ valid,
                    double* __restrict__ pair_acc, double* __restrict__ energy, const __grid_constant__ PeerGroup pg,
-                   uint64_t* __restrict__ seq_counter, unsigned int* __restrict__ ticket) {
+                   uint64_t* __restrict__ seq_counter, unsigned int* __restrict__ ticket, const SelectArgs sel) {
     const int64_t per_rank = (int64_t)S * P * 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int warps = kTailThreads / 32;
@@ -547,6 +559,11 @@ energy_tail_kernel(const double* __restrict__ cta_partial, int n_ctas, int S, in
     if (threadIdx.x == 0) {
         *seq_counter = seq;
         *ticket = 0;                                          // self-cleaning for the next launch
+    }
+    if (sel.pop) {                                            // the DE selection of this generation, same block
+        __syncthreads();
+        de::select_block(sel.pop, sel.energies, sel.trial, energy, sel.n_members, sel.n_params, sel.tol, sel.atol,
+                         sel.generation, sel.status, sel.best);
     }
 }
 
@@ -709,7 +726,7 @@ size_t cl_icrf_exchange_bytes(const cl_icrf_problem* p, int world) {
 int cl_icrf_energy_population(const cl_icrf_problem* p, const void* tables, const uint8_t* dn, const double* std,
                               const double* exposure_s, int64_t n_pixels, const int32_t* valid, double* pair_acc,
                               double* energy, void* workspace, size_t workspace_bytes, const cl_peer_group* peers,
-                              void* stream) {
+                              const cl_de_select_args* select, void* stream) {
     using namespace cl;
     if (!problem_ok(p)) return CL_ERR_INVALID_ARGUMENT;
     CL_REQUIRE(tables && exposure_s && valid && pair_acc && energy && n_pixels >= 1 && dn && peers);
@@ -736,9 +753,18 @@ int cl_icrf_energy_population(const cl_icrf_problem* p, const void* tables, cons
     const int64_t outputs = (int64_t)p->n_candidates * P * 2;
     int blocks = (int)((outputs + (kTailThreads / 32) - 1) / (kTailThreads / 32));
     if (blocks > 148) blocks = 148;
+    SelectArgs sel;
+    memset(&sel, 0, sizeof(sel));
+    if (select) {
+        CL_REQUIRE(select->pop && select->energies && select->trial && select->generation && select->status && select->best);
+        CL_REQUIRE(select->n_members >= 4 && select->n_members <= p->n_candidates && select->n_params == p->n_params);
+        sel.pop = select->pop; sel.energies = select->energies; sel.trial = select->trial;
+        sel.n_members = select->n_members; sel.n_params = select->n_params; sel.tol = select->tol; sel.atol = select->atol;
+        sel.generation = select->generation; sel.status = select->status; sel.best = select->best;
+    }
     energy_tail_kernel<<<blocks, kTailThreads, 0, s>>>(cta_partial, pl.chunks, p->n_candidates, P, valid, pair_acc, energy,
                                                        pg, reinterpret_cast<uint64_t*>(tail),
-                                                       reinterpret_cast<unsigned int*>(tail + 8));
+                                                       reinterpret_cast<unsigned int*>(tail + 8), sel);
     return launched();
 }
 

@@ -156,11 +156,32 @@ class Measurand:
         return x1, x2, s1, s2, use_std
 
     # ---- arithmetic with uncertainty propagation (measurand.py:106-241) ----
+    # On the device every operator is ONE fused kernel (csrc/measurand_ops.cu: the reference's 4-10 ufunc passes
+    # become one); the torch expressions below are the same formulae for host tensors (contract tests) and for
+    # operand shapes the kernel does not take (general broadcasting, non-float64 data).
+    def _fused(self, op: str, other):
+        normalized, _ = self._normalize_input(other)
+        x1, x2 = self.val, normalized.val
+        if not gf.is_broadcastable(x1.shape, x2.shape):
+            raise ValueError('Measurands are not broadcastable.')
+        if not (x1.is_cuda and x1.dtype == torch.float64 and x2.dtype == torch.float64 and x1.numel() > 0):
+            return None
+        if ops.suffix_period(x1.shape, x2.shape) is None:
+            return None
+        v, s = ops.measurand_binary(op, x1, self.std, x2, normalized.std)
+        return self.__class__(v, s)
+
     def __add__(self, other):
+        fused = self._fused("add", other)
+        if fused is not None:
+            return fused
         x1, x2, s1, s2, use_std = self._binary_operands(other)
         return self.__class__(x1 + x2, torch.sqrt(s1 ** 2 + s2 ** 2) if use_std else None)
 
     def __sub__(self, other):
+        fused = self._fused("sub", other)
+        if fused is not None:
+            return fused
         x1, x2, s1, s2, use_std = self._binary_operands(other)
         return self.__class__(x1 - x2, torch.sqrt(s1 ** 2 + s2 ** 2) if use_std else None)
 
@@ -168,6 +189,9 @@ class Measurand:
         return self.__class__(torch.negative(self.val), None if self.std is None else self.std.clone())
 
     def __truediv__(self, other):
+        fused = self._fused("div", other)
+        if fused is not None:
+            return fused
         x1, x2, s1, s2, use_std = self._binary_operands(other)
         if not use_std:
             return self.__class__(x1 / x2, None)
@@ -176,6 +200,9 @@ class Measurand:
         return self.__class__(x1 / x2, torch.sqrt(u1 ** 2 + u2 ** 2))
 
     def __mul__(self, other):
+        fused = self._fused("mul", other)
+        if fused is not None:
+            return fused
         x1, x2, s1, s2, use_std = self._binary_operands(other)
         if not use_std:
             return self.__class__(x1 * x2, None)
@@ -185,6 +212,9 @@ class Measurand:
         return self * self.__class__(other)
 
     def __pow__(self, other):
+        fused = self._fused("pow", other)
+        if fused is not None:
+            return fused
         x1, x2, s1, s2, use_std = self._binary_operands(other)
         if not use_std:
             return self.__class__(x1 ** x2, None)
@@ -194,10 +224,14 @@ class Measurand:
 
     def log_e(self):
         # literal reference formula (measurand.py:258), questionable maths kept (D18)
+        if self.val.is_cuda and self.val.dtype == torch.float64 and self.val.numel() > 0:
+            return self.__class__(*ops.measurand_log(self.val, self.std, False))
         res = torch.log(self.val)
         return self.__class__(res, None if self.std is None else self.std / torch.log(self.val))
 
     def log_10(self):
+        if self.val.is_cuda and self.val.dtype == torch.float64 and self.val.numel() > 0:
+            return self.__class__(*ops.measurand_log(self.val, self.std, True))
         res = torch.log10(self.val)
         if self.std is None:
             return self.__class__(res, None)
@@ -311,6 +345,10 @@ class Measurand:
     @staticmethod
     def compute_difference(x: 'Measurand', y: 'Measurand', multiplier: float):
         cls = x.__class__
+        if (x.val.is_cuda and x.val.dtype == torch.float64 and y.val.dtype == torch.float64
+                and x.val.shape == y.val.shape and x.val.numel() > 0):
+            av, a_s, rv, r_s = ops.measurand_difference(x.val, x.std, y.val, y.std, multiplier)
+            return cls(av, a_s), cls(rv, r_s)
         scale_term = multiplier * y.val
         abs_diff = x.val - scale_term
         rel_diff = abs_diff / scale_term

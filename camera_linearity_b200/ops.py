@@ -519,15 +519,17 @@ class IcrfEnergyPlan:
         return self.energy[: self.n_real]
 
     @_plan_device
-    def population(self) -> Tensor:
+    def population(self, select=None) -> Tensor:
         """Partial kernel + fused tail (CTA reduction, exchange with the attached peers, finalize): the energies
-        of the candidates whose curves / tables are current, over the pixels of ALL ranks."""
+        of the candidates whose curves / tables are current, over the pixels of ALL ranks.  ``select``: a
+        ``_lib.DeSelectArgs`` -- the DE selection of the generation then runs in the same launch."""
         if self.n_pixels == 0:
             raise ValueError("population() needs at least one pixel on every rank")
         check(self.lib.cl_icrf_energy_population(C.byref(self.prob), _ptr(self.tables), _ptr(self.dn), _ptr(self.std),
                                                  self.exposures, self.n_pixels, _ptr(self.valid), _ptr(self.pair_acc),
                                                  _ptr(self.energy), _ptr(self.ws), self.ws_bytes, C.byref(self.peers),
-                                                 _stream()), "cl_icrf_energy_population")
+                                                 None if select is None else C.byref(select), _stream()),
+              "cl_icrf_energy_population")
         return self.energy[: self.n_real]
 
     def evaluate(self, params) -> Tensor:
@@ -584,12 +586,13 @@ class DeviceDE:
     @classmethod
     def for_plan(cls, plan: "IcrfEnergyPlan", lower, upper, init_unit_population: Tensor, seed: int, **kw):
         """DE whose objective is ``plan`` (K4).  One generation = ``cl_de_trial_curves`` (trial vectors + candidate
-        curves), ``cl_icrf_energy_population`` (partial kernel + fused reduce / peer exchange / finalize) and
-        ``cl_de_select``: four kernels, no NCCL launch, nothing on the host."""
+        curves) and ``cl_icrf_energy_population`` (partial kernel + fused reduce / peer exchange / finalize /
+        DE selection): three kernels, no NCCL launch, nothing on the host."""
         if plan.n_real != init_unit_population.shape[0] or plan.prob.n_params != init_unit_population.shape[1]:
             raise ValueError("the plan must be built for exactly this population")
         self = cls(lambda params: plan.evaluate(params), lower, upper, init_unit_population, seed, **kw)
         self.plan = plan
+        self._select = None
         self._graph = None
         self._graph_steps = 0
         return self
@@ -602,10 +605,13 @@ class DeviceDE:
                                           _ptr(self.lower), _ptr(self.upper), _ptr(self.trial), _ptr(plan.params),
                                           _ptr(plan.mean), _ptr(plan.pca), _ptr(plan.curves), _ptr(plan.valid),
                                           _ptr(plan.tables), _stream()), "cl_de_trial_curves")
-        trial_energies = plan.population()
-        check(self.lib.cl_de_select(_ptr(self.pop), _ptr(self.energies), _ptr(self.trial), _ptr(trial_energies),
-                                    self.S, self.P, self.tol, self.atol, _ptr(self.generation), _ptr(self.status),
-                                    _ptr(self.best), _stream()), "cl_de_select")
+        if self._select is None:
+            sel = _lib.DeSelectArgs()
+            sel.pop, sel.energies, sel.trial = _ptr(self.pop), _ptr(self.energies), _ptr(self.trial)
+            sel.n_members, sel.n_params, sel.tol, sel.atol = self.S, self.P, self.tol, self.atol
+            sel.generation, sel.status, sel.best = _ptr(self.generation), _ptr(self.status), _ptr(self.best)
+            self._select = sel
+        plan.population(self._select)            # ... -> finalize -> selection, in the tail kernel's last block
 
     def run_graph(self, generations: int, per_graph: int = 8) -> None:
         """Advance ``generations`` generations (a multiple of ``per_graph``) by replaying a CUDA graph of
@@ -666,6 +672,97 @@ def pair_statistics(x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor, y_std
     check(lib.cl_pair_statistics(_ptr(xv), _ptr(xs), _ptr(yv), _ptr(ys), float(multiplier), lo, hi, xv.numel(), c,
                                  _ptr(stats), _ptr(ws), ws_bytes, _stream()), "cl_pair_statistics")
     return stats
+
+
+# ------------------------------------------------------------------------------------- Measurand operators
+_BINARY_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "pow": 4}
+
+
+def suffix_period(x_shape, y_shape) -> Optional[int]:
+    """``y`` pairs with ``x`` element i <-> i % period when its shape is the same as ``x``'s, or equals ``x``'s trailing
+    dimensions (after dropping leading 1s): a per-channel vector, a scalar.  Returns the period or None."""
+    xs, ys = tuple(x_shape), tuple(y_shape)
+    while ys and ys[0] == 1 and len(ys) > 1:
+        ys = ys[1:]
+    if ys == (1,) or ys == ():
+        return 1
+    if len(ys) <= len(xs) and xs[len(xs) - len(ys):] == ys:
+        n = 1
+        for d in ys:
+            n *= int(d)
+        return n
+    return None
+
+
+@_on_device
+def measurand_binary(op: str, x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor, y_std: Optional[Tensor]):
+    """``x (op) y`` with first-order uncertainty propagation (measurand.py:106-241), one fused pass.  ``y`` must be
+    the same shape as ``x`` or a suffix operand (see ``suffix_period``).  Returns (val, std or None)."""
+    _require_cuda(x_val, x_std, y_val, y_std)
+    lib = _lib.load()
+    period = suffix_period(x_val.shape, y_val.shape)
+    if period is None or x_val.numel() == 0:
+        raise ValueError("measurand_binary needs y to be the same shape as x or a suffix of it")
+    xv, xs, yv, ys = _f64c(x_val), _f64c(x_std), _f64c(y_val), _f64c(y_std)
+    use_std = xs is not None or ys is not None
+    out_v = torch.empty_like(xv)
+    out_s = torch.empty_like(xv) if use_std else None
+    check(lib.cl_measurand_binary(_BINARY_OPS[op], _ptr(xv), _ptr(xs), _ptr(yv), _ptr(ys), xv.numel(), int(period),
+                                  _ptr(out_v), _ptr(out_s), _stream()), "cl_measurand_binary")
+    return out_v, out_s
+
+
+@_on_device
+def measurand_log(val: Tensor, std: Optional[Tensor], base10: bool):
+    """``log_e`` / ``log_10`` with the reference's literal uncertainty formulae (measurand.py:243-279)."""
+    _require_cuda(val, std)
+    lib = _lib.load()
+    v, s = _f64c(val), _f64c(std)
+    out_v = torch.empty_like(v)
+    out_s = torch.empty_like(v) if s is not None else None
+    check(lib.cl_measurand_log(1 if base10 else 0, _ptr(v), _ptr(s), v.numel(), _ptr(out_v), _ptr(out_s), _stream()),
+          "cl_measurand_log")
+    return out_v, out_s
+
+
+@_on_device
+def measurand_difference(x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor, y_std: Optional[Tensor],
+                         multiplier: float):
+    """``compute_difference`` (measurand.py:620-655): returns (abs_val, abs_std, rel_val, rel_std), one pass."""
+    _require_cuda(x_val, x_std, y_val, y_std)
+    lib = _lib.load()
+    if x_val.shape != y_val.shape:
+        raise ValueError('Measurands are not broadcastable.')
+    xv, xs, yv, ys = _f64c(x_val), _f64c(x_std), _f64c(y_val), _f64c(y_std)
+    use_std = xs is not None or ys is not None
+    av, rv = torch.empty_like(xv), torch.empty_like(xv)
+    a_s = torch.empty_like(xv) if use_std else None
+    r_s = torch.empty_like(xv) if use_std else None
+    check(lib.cl_measurand_difference(_ptr(xv), _ptr(xs), _ptr(yv), _ptr(ys), float(multiplier), xv.numel(), _ptr(av),
+                                      _ptr(a_s), _ptr(rv), _ptr(r_s), _stream()), "cl_measurand_difference")
+    return av, a_s, rv, r_s
+
+
+# ------------------------------------------------------------------------------------- noise profiles
+@_on_device
+def noise_profiles(frames: Tensor, mean_u8: Tensor, hist: Optional[Tensor] = None) -> Tensor:
+    """Accumulate the joint (mean DN, frame DN) histogram per channel of ``frames`` (F, H, W, C) uint8 against the uint8
+    mean frame (video_processing.py:92-104).  ``hist``: int64 (256, 256, C), created zeroed when not given."""
+    _require_cuda(frames, mean_u8, hist)
+    lib = _lib.load()
+    if frames.dtype != torch.uint8 or mean_u8.dtype != torch.uint8 or frames.ndim < 2:
+        raise TypeError("frames and the mean frame must be uint8")
+    fr, mu = frames.contiguous(), mean_u8.contiguous()
+    if tuple(fr.shape[1:]) != tuple(mu.shape):
+        raise ValueError("the mean frame must have the shape of one frame")
+    c = int(fr.shape[-1])
+    if hist is None:
+        hist = torch.zeros((256, 256, c), dtype=torch.int64, device=fr.device)
+    elif hist.dtype != torch.int64 or tuple(hist.shape) != (256, 256, c) or not hist.is_contiguous():
+        raise ValueError("hist must be a contiguous int64 (256, 256, C) tensor")
+    check(lib.cl_noise_profiles(_ptr(fr), int(fr.shape[0]), mu.numel(), c, _ptr(mu), _ptr(hist), _stream()),
+          "cl_noise_profiles")
+    return hist
 
 
 # ------------------------------------------------------------------------------------- histogram

@@ -119,6 +119,42 @@ def welford_algorithm(file_paths: Union[Path, List[Path]], ICRF=None, use_std: O
     return {'mean': mean_u8, 'std': std_u8, 'mean_f64': mean, 'sem': sem, 'count': count}
 
 
+def compute_noise_profiles(video_files: List[Path], frame_source=None):
+    """Noise profiles of a camera from videos of a static scene (video_processing.py:77-106): the joint histogram
+    ``profiles[mean DN, frame DN, channel]`` over every frame, against the uint8 Welford mean frame.  Returns
+    ``(profiles int64 (BITS, BITS, C) tensor, mean frame uint8 tensor)``.  Frames are decoded on the host into a pinned
+    chunk buffer and binned on the device (``cl_noise_profiles``); 8-bit data (the reference indexes the profile
+    with the frame bytes)."""
+    if not isinstance(video_files, list):
+        video_files = [video_files]
+    source = gf.video_frame_generator if frame_source is None else frame_source
+    mean_frame = welford_algorithm(video_files, None, False, frame_source=frame_source)['mean']       # :90
+    dev = mean_frame.device
+    hist = None
+    shape = (CHUNK_FRAMES,) + tuple(mean_frame.shape)
+    host = torch.empty(shape, dtype=torch.uint8, pin_memory=dev.type == "cuda")
+    host_np = host.numpy()
+    fill = 0
+
+    def flush(n):
+        nonlocal hist
+        if n:
+            hist = ops.noise_profiles(host[:n].to(dev), mean_frame, hist)   # (synchronous copy: the buffer is reused)
+    for video_file in video_files:                                                                  # :92-104
+        for frame in source(video_file):
+            if frame is None:
+                break
+            host_np[fill] = frame
+            fill += 1
+            if fill == CHUNK_FRAMES:
+                flush(fill)
+                fill = 0
+    flush(fill)
+    if hist is None:
+        raise ValueError("no frames decoded")
+    return hist, mean_frame
+
+
 def process_video(video_path: Path, ICRF=None, use_std: Optional[bool] = True):
     """video_processing.py:222-236."""
     import cv2 as cv

@@ -222,11 +222,24 @@ typedef struct cl_peer_group {
     int32_t world, rank;
     void* buffers[CL_MAX_PEERS];
 } cl_peer_group;
+/* select != NULL: the differential-evolution selection of this generation (what cl_de_select does, see below) runs in
+ * the same launch right after the finalize, with the energies just computed as the trial energies. */
+typedef struct cl_de_select_args {
+    double* pop;              /* device [n_members][n_params], unit cube */
+    double* energies;         /* device [n_members] */
+    const double* trial;      /* device [n_members][n_params] */
+    int32_t n_members, n_params;
+    double tol, atol;
+    int64_t* generation;      /* device counter, incremented */
+    int32_t* status;          /* device [4] */
+    double* best;             /* device [3] */
+} cl_de_select_args;
 size_t cl_icrf_exchange_bytes(const cl_icrf_problem* p, int world);
 int cl_icrf_energy_population(const cl_icrf_problem* p, const void* tables, const uint8_t* dn, const double* std,
                               const double* exposure_s /* HOST [N] */, int64_t n_pixels, const int32_t* valid,
                               double* pair_acc, double* energy, void* workspace, size_t workspace_bytes,
-                              const cl_peer_group* peers, void* stream);
+                              const cl_peer_group* peers, const cl_de_select_args* select /* nullable */,
+                              void* stream);
 
 /* Peer-visible device buffers (CUDA IPC) for the exchange above: cl_peer_alloc on the owning rank (cudaMalloc,
  * zero-filled, synchronous), the 64-byte handle travels to the other processes by any means
@@ -293,6 +306,31 @@ int cl_de_trial_curves(const cl_icrf_problem* p, const double* pop, int n_member
 int cl_de_select(double* pop, double* energies, const double* trial, const double* trial_energies,
                  int n_members, int n_params, double tol, double atol, int64_t* generation, int32_t* status,
                  double* best, void* stream);
+
+/* ---- Measurand operators with uncertainty propagation --------------------------------
+ * One fused streaming pass per operator instead of the reference's chain of NumPy ufuncs
+ * (modules/measurand.py:106-241 operators, :243-279 logarithms, :620-655 compute_difference).
+ *   cl_measurand_binary: op 0 add, 1 sub, 2 mul, 3 div, 4 pow;  out = x (op) y with std per the reference formulae.
+ *     y_period == n: same shape; otherwise y is a "suffix" operand (per-channel vector, scalar): element i of x
+ *     pairs with element i % y_period of y.  x_std / y_std may be NULL (taken as zeros); out_std == NULL: values only.
+ *   cl_measurand_log: base10 == 0: log(x), std / log(x) (the reference's literal formula); 1: log10(x),
+ *     std / (x (log 5 + log 2)).
+ *   cl_measurand_difference: abs = x - m y, rel = abs / (m y), and their uncertainties when any std is given. */
+int cl_measurand_binary(int op, const double* x_val, const double* x_std, const double* y_val, const double* y_std,
+                        int64_t n, int64_t y_period, double* out_val, double* out_std, void* stream);
+int cl_measurand_log(int base10, const double* val, const double* std, int64_t n, double* out_val, double* out_std,
+                     void* stream);
+int cl_measurand_difference(const double* x_val, const double* x_std, const double* y_val, const double* y_std,
+                            double multiplier, int64_t n, double* abs_val, double* abs_std, double* rel_val,
+                            double* rel_std, void* stream);
+
+/* ---- Camera noise profiles ---------------------------------------------------------------------------------
+ * Replaces the scatter loop of compute_noise_profiles (modules/video_processing.py:92-104): for every sample of
+ * every frame, hist[mean_u8[sample]][frame[sample]][channel] += 1.  frames: device [n_frames][n_samples] uint8
+ * (channel-interleaved images), mean_u8: device [n_samples] (the uint8 mean frame of welford_algorithm), hist: device
+ * int64 [256][256][channels], ACCUMULATED into (the caller clears it once and may feed the video in chunks). */
+int cl_noise_profiles(const uint8_t* frames, int n_frames, int64_t n_samples, int channels, const uint8_t* mean_u8,
+                      int64_t* hist, void* stream);
 
 /* ---- Per-channel histogram -------------------------------------------------------------------------
  * Replaces the array part of compute_channel_histogram (modules/measurand.py:430-469): np.histogram of

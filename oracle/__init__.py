@@ -26,4 +26,4 @@ Parity status of this oracle (see DESIGN.md section 3 and ``tests/test_oracle_go
   own tests hold no golden vectors for any of K1..K4.
 """
 
-from . import linearize, hdr_merge, welford, icrf_energy, linearity, egress, de, histogram  # noqa: F401
+from . import linearize, hdr_merge, welford, icrf_energy, linearity, egress, de, histogram, noise_profiles  # noqa: F401

@@ -305,6 +305,39 @@ def golden_welford(ref):
                         std_u8=r3['std'], katw_mean_u8=r4['mean'], katw_std_u8=r4['std'])
 
 
+def golden_noise_profiles(ref):
+    """UNMODIFIED ``compute_noise_profiles`` (video_processing.py:77-106): joint histogram of (uint8 mean frame DN,
+    frame DN) per channel over every frame of the videos; only the frame source is replaced."""
+    vp = ref.video_processing
+
+    class _Cap:
+        def __init__(self, shape):
+            self.shape = shape
+
+        def get(self, prop):
+            import cv2
+            return self.shape[1] if prop == cv2.CAP_PROP_FRAME_WIDTH else self.shape[0]
+
+    rng = np.random.default_rng(91)
+    base = rng.integers(0, 256, (24, 20, 3))
+    base[:3] = 0                                   # clipped ends: rows whose noise leaves [0, 255]
+    base[3:6] = 255
+    videos = [[np.clip(base + np.rint(rng.normal(0, 2.5, base.shape)).astype(int), 0, 255).astype(np.uint8)
+               for _ in range(n)] for n in (9, 6)]
+    # one pixel with a wild outlier far from its mean (outside any small window around the mean)
+    videos[0][4][10, 10, 1] = 255 if base[10, 10, 1] < 128 else 0
+
+    def gen(path):
+        for f in videos[int(Path(path).stem)]:
+            yield f
+        yield None
+    vp.gf.video_frame_generator = gen
+    vp.cv.VideoCapture = lambda p: _Cap(base.shape)
+    profiles, mean_frame = vp.compute_noise_profiles([Path('/tmp/0.avi'), Path('/tmp/1.avi')])
+    np.savez_compressed(OUT / 'k9_noise_profiles.npz', frames0=np.stack(videos[0]), frames1=np.stack(videos[1]),
+                        profiles=profiles, mean_frame=mean_frame)
+
+
 # ----------------------------------------------------------------------------- K4
 def golden_energy(ref):
     ice = ref.ICRF_calibration_exposure
@@ -447,6 +480,7 @@ if __name__ == '__main__':
     ref = ref_loader.load()
     golden_linearize(ref)
     golden_welford(ref)
+    golden_noise_profiles(ref)
     golden_energy(ref)
     golden_linearity(ref)
     golden_save_8bit(ref)

@@ -242,3 +242,14 @@ def test_welford_with_icrf_matches_the_unmodified_reference(golden_dir):
     katw = [((31 * hh + 17 * ww + 5 * cc + 3 * f * f + f * hh) % 256).astype(np.uint8) for f in range(7)]
     r = ow.welford(katw, g["icrf"])
     assert np.array_equal(r["mean_u8"], g["katw_mean_u8"]) and np.array_equal(r["std_u8"], g["katw_std_u8"])
+
+
+def test_noise_profiles_match_the_unmodified_reference(golden_dir):
+    """compute_noise_profiles (video_processing.py:77-106) run unmodified in make_golden.py: joint histogram of
+    (uint8 mean DN, frame DN) per channel over both videos -- integer work, bit-exact."""
+    from oracle import noise_profiles as onp
+    g = np.load(golden_dir / "k9_noise_profiles.npz")
+    profiles, mean_frame = onp.noise_profiles([list(g["frames0"]), list(g["frames1"])])
+    assert np.array_equal(mean_frame, g["mean_frame"])
+    assert profiles.dtype == np.int64 and np.array_equal(profiles, g["profiles"])
+    assert profiles.sum() == (len(g["frames0"]) + len(g["frames1"])) * g["mean_frame"].size
