@@ -880,7 +880,15 @@ def extra_kernels(dev):
     ms = timed(lambda: ops.pair_statistics(xv, xs, yv, ys, 0.5, [0.1] * 3, [0.9] * 3))
     out["pair_statistics"] = {"ms": ms, "GB/s": xv.numel() * 32 / ms / 1e6, "frac_of_hbm_peak": xv.numel() * 32 / ms / 1e6 / peak,
                               "shape": "one exposure pair 2160x3840x3 f64 val+std, every input read once (32 B/sample)"}
-    del xv, yv, xs, ys
+    # Measurand operators with propagation, fused (measurand.py:106-241): x * y and x / y on 4K RGB val+std pairs,
+    # 32 B in + 16 B out per element
+    import camera_linearity_b200 as cl
+    mx, my = cl.Measurand(xv, xs), cl.Measurand(yv, ys)
+    for name, fn in (("measurand_mul", lambda: mx * my), ("measurand_div", lambda: mx / my)):
+        ms = timed(fn)
+        out[name] = {"ms": ms, "GB/s": xv.numel() * 48 / ms / 1e6, "frac_of_hbm_peak": xv.numel() * 48 / ms / 1e6 / peak,
+                     "shape": "2160x3840x3 f64 val+std (op) same, one fused pass"}
+    del mx, my, xv, yv, xs, ys
     # K3: cfg4, 600 frames 1080x1920x3
     base = torch.randint(20, 231, (1, 1080, 1920, 3), generator=g, device=dev, dtype=torch.int16)
     frames = torch.empty((600, 1080, 1920, 3), dtype=torch.uint8, device=dev)
@@ -897,6 +905,13 @@ def extra_kernels(dev):
     ms = timed(lambda: ops.welford_stack(frames, icrf, 255.0, ws), reps=3, warm=1)       # linearised frames (ICRF given)
     out["k3_welford_stack_icrf"] = {"ms": ms, "GB/s": nb / ms / 1e6, "frac_of_hbm_peak": nb / ms / 1e6 / peak,
                                     "shape": "cfg4 with ICRF[frame, c] as the sample value"}
+    # noise profiles (joint mean-DN / frame-DN histogram per channel, video_processing.py:77-106) over the same 600 frames
+    mean_u8 = ops.welford_stack(frames, None, 255.0, ws)[2]
+    hist = torch.zeros((256, 256, 3), dtype=torch.int64, device=dev)
+    ms = timed(lambda: ops.noise_profiles(frames, mean_u8, hist), reps=3, warm=1)
+    out["noise_profiles"] = {"ms": ms, "GB/s": frames.numel() / ms / 1e6, "frac_of_hbm_peak": frames.numel() / ms / 1e6 / peak,
+                             "shape": "cfg4 frames against their uint8 mean frame, 1 B per sample-frame"}
+    del hist, mean_u8
     # the reference's Welford recurrence (oracle port of video_processing.py:183-217) on a bounded number of frames
     from oracle import welford as ow
     n_f = 12

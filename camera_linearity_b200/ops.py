@@ -969,3 +969,16 @@ def _op_pair_statistics(x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor, y
 def _op_quantize_8bit(val: Tensor, max_dn: float) -> List[Tensor]:
     out, mx = quantize_8bit(val, max_dn, return_max=True)
     return [out, mx]
+
+
+@torch.library.custom_op("camera_linearity::noise_profiles", mutates_args=(), device_types="cuda")
+def _op_noise_profiles(frames: Tensor, mean_u8: Tensor) -> Tensor:
+    return noise_profiles(frames, mean_u8)
+
+
+@torch.library.custom_op("camera_linearity::measurand_binary", mutates_args=(), device_types="cuda")
+def _op_measurand_binary(op: str, x_val: Tensor, x_std: Optional[Tensor], y_val: Tensor,
+                         y_std: Optional[Tensor]) -> List[Tensor]:
+    """op in add / sub / mul / div / pow; returns [val] or [val, std]."""
+    v, s_ = measurand_binary(op, x_val, x_std, y_val, y_std)
+    return [v] if s_ is None else [v, s_]

@@ -22,7 +22,7 @@ TIGHT = 1e-11
 def test_registered_surface():
     for name in ("linearize", "hdr_merge", "hdr_merge_corrected", "flat_roi_means", "welford_stack", "welford_update",
                  "welford_finalize", "gaussian_weight", "icrf_energy_curves", "icrf_energy_partial",
-                 "icrf_energy_finalize", "pair_statistics", "quantize_8bit"):
+                 "icrf_energy_finalize", "pair_statistics", "quantize_8bit", "noise_profiles", "measurand_binary"):
         assert hasattr(K, name), name
 
 
@@ -138,3 +138,17 @@ def test_operators_follow_the_device_of_their_tensors():
     ev, _ = ol.linearize(img, None, icrf, None)
     assert np.array_equal(v.cpu().numpy(), ev)
     assert torch.cuda.current_device() == 0
+
+
+def test_noise_profiles_and_measurand_binary_ops():
+    from oracle import noise_profiles as onp
+    rng = np.random.default_rng(26)
+    base = rng.integers(0, 256, (20, 24, 3))
+    video = [np.clip(base + rng.integers(-4, 5, base.shape), 0, 255).astype(np.uint8) for _ in range(11)]
+    exp, mean_frame = onp.noise_profiles([video])
+    assert np.array_equal(host(K.noise_profiles(dev(np.stack(video)), dev(mean_frame))), exp)
+    x, xs = rng.uniform(0.1, 2, (20, 24, 3)), rng.uniform(0.001, 0.05, (20, 24, 3))
+    y, ys = rng.uniform(0.5, 1.5, (3,)), rng.uniform(0.001, 0.05, (3,))
+    v, s = K.measurand_binary("div", dev(x), dev(xs), dev(y), dev(ys))
+    assert np.array_equal(host(v), x / y)
+    assert np.array_equal(host(s), np.sqrt((xs / y) ** 2 + ((x * ys) / (y ** 2)) ** 2))
