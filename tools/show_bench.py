@@ -10,7 +10,7 @@ for path in sys.argv[1:]:
     e = d["e2e"]
     print(f"   e2e {e['value']:.2f} ({e['ms_per_step']:.1f} ms/step)", end="")
     sv = d.get("std_table_variant")
-    if sv:
+    if sv and "e2e" in sv:
         print(f" | STD-table: {sv['value']:.1f} dev ({sv['ms_per_step']:.4f} ms), e2e {sv['e2e']['value']:.2f} "
               f"({sv['e2e']['ms_per_step']:.2f} ms/step)", end="")
     print()
