@@ -375,19 +375,67 @@ __device__ __noinline__ void recompute_sample(const MergeParams& p, int64_t i) {
     p.out_std[i] = os;
 }
 
+// The single-pass kernel's rule for one sample (hdr_merge_stream.cu): the expanded variance, unless it cancelled
+// (q < kStreamCancel * A), in which case the exact two-pass formula.  Same operations in the same order as the
+// kernel, so a sample gets the same bits whichever of the two computes it.
+__device__ __noinline__ void recompute_sample_stream(const MergeParams& p, int64_t i) {
+    const int C = p.C;
+    const int c = (int)(i % C);
+    const int64_t px = i / C;
+    const int y = (int)(px / p.W), x = (int)(px - (int64_t)y * p.W);
+    double S = 0.0, av = 0.0, A = 0.0, B = 0.0, Cc = 0.0;
+    for (int k = 0; k < p.n; ++k) {
+        const uint8_t* img = reinterpret_cast<const uint8_t*>(p.dn[k]);
+        uint32_t d = img[i];
+        double sg = p.std[k][i];
+        if (p.dark[k] && (uint32_t) reinterpret_cast<const uint8_t*>(p.dark[k])[i] >= p.hot_dn[k]) {
+            d = median_dn(img, y, x, c, p.H, p.W, C, p.K);
+            sg = median_std(p.std[k], img, p.std_lut, y, x, c, p.H, p.W, C, p.K);
+        }
+        double w, dw;
+        gaussian_weight(__ddiv_rn((double)d, p.max_dn), w, dw);
+        const double p1 = w * p.lut[(int64_t)d * C + c];
+        merge_accumulate_expanded(w, p1, p.dlut[(int64_t)d * C + c], kappa_of(d, p.kappa_scale), sg, p.inv_t[k], S, av,
+                                  A, B, Cc);
+    }
+    const double rS = 1.0 / S;
+    const double q = expanded_variance(A, B, Cc, rS);
+    if (q < kStreamCancel * A) {
+        recompute_sample<uint8_t>(p, i);
+        return;
+    }
+    double ov = av * rS, os;
+    if (p.flat_bytes)
+        flat_apply(ov, os, (q * rS) * rS, flat_recip(p.flat, p.flat_bytes, i, p.max_dn), p.flat_std[i],
+                   p.flat_means[c], p.flat_means[C + c]);
+    else
+        os = sqrt(q) * rS;
+    p.out_val[i] = ov;
+    p.out_std[i] = os;
+}
+
 __global__ void __launch_bounds__(128)
 merge_fixup_kernel(const __grid_constant__ MergeParams p) {
     const uint32_t count = p.hot_list[0];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (count <= p.hot_cap) {
-        for (int64_t t = tid; t < count; t += stride)
-            recompute_sample<uint8_t>(p, (int64_t)p.hot_list[kHotListHeader + t]);
+        for (int64_t t = tid; t < count; t += stride) {
+            const int64_t i = (int64_t)p.hot_list[kHotListHeader + t];
+            if (p.stream_mode) recompute_sample_stream(p, i);
+            else recompute_sample<uint8_t>(p, i);
+        }
         return;
     }
-    // the list overflowed (pathological: most of the image is "bad"): rescan every sample
+    // the list overflowed (pathological: most of the image is "bad", or most of it cancels in the single-pass
+    // kernel): rescan every full-tile sample
     const int64_t n = (int64_t)p.H * p.W * p.C;
+    const int64_t n_stream = p.stream_mode ? (int64_t)p.n_full_tiles * kStagedTilePx * 3 : 0;
     for (int64_t i = tid; i < n; i += stride) {
+        if (i < n_stream) {
+            recompute_sample_stream(p, i);
+            continue;
+        }
         bool any = false;
         for (int k = 0; k < p.n && !any; ++k)
             any = p.dark[k] && reinterpret_cast<const uint8_t*>(p.dark[k])[i] >= p.hot_dn[k];
@@ -581,6 +629,10 @@ size_t bucket_bytes(int64_t n_pixels) {
     return (size_t)(n_pixels / kStagedTilePx) * kBucketWords * sizeof(uint32_t);
 }
 
+int clear_hot_list(const MergeParams& p, cudaStream_t stream) {
+    return cuda_status(cudaMemsetAsync(p.hot_list, 0, kHotListHeader * sizeof(uint32_t), stream));
+}
+
 int launch_merge_fixup(const MergeParams& p, cudaStream_t stream) {
     merge_fixup_kernel<<<sm_count() * 8, 128, 0, stream>>>(p);
     return launched();
@@ -604,11 +656,9 @@ size_t cl_hdr_merge_workspace_bytes(const cl_hdr_merge_args* a) {
         const size_t wide = cl::wide_table_bytes(a->bits, a->channels, a->std_lut != nullptr);
         bytes += generic > wide ? generic : wide;
     }
-    // bad-pixel work list of the staged kernel (uint8, 3 channels, dark frames present)
-    bool any_dark = false;
-    if (a->dark)
-        for (int k = 0; k < a->n_exposures && k < CL_MAX_EXPOSURES; ++k) any_dark |= a->dark[k] != nullptr;
-    if (any_dark && a->dn_bytes == 1 && (a->channels == 3 || a->channels == 1) && a->algo != 1)
+    // work list (bad pixels whose tile bucket overflowed; samples the single-pass kernel hands to the exact two-pass
+    // formula) + per-tile bad-pixel buckets of the 8-bit RGB / mono fast kernels
+    if (a->dn_bytes == 1 && (a->channels == 3 || a->channels == 1) && a->algo != 1)
         bytes += (cl::kHotListHeader + cl::hot_list_entries((int64_t)a->height * a->width * a->channels)) *
                      sizeof(uint32_t) +
                  cl::bucket_bytes((int64_t)a->height * a->width * a->channels / 3) + 16;
@@ -678,7 +728,7 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
     const bool tab_smem = a->bits <= 256;
     // 16-bit stacks with uncertainty images and N <= 16: fused-table kernel (hdr_merge_wide.cu)
     bool wide = false;
-    if (!tab_smem && a->algo != 1 && a->algo != 2) {
+    if (!tab_smem && a->algo != 1 && a->algo != 2 && a->algo != 4) {
         if (workspace && aligned(workspace, 32) && workspace_bytes >= wide_table_bytes(p.bits, p.C, !all_std))
             p.g_tab32 = reinterpret_cast<const double2*>(workspace);
         wide = merge_wide_supported(p, a->dn_bytes, all_std);
@@ -701,7 +751,7 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
         p.g_pb = pb;
     }
 
-    if (p.any_dark && a->dn_bytes == 1 && (p.C == 3 || p.C == 1) && a->algo != 1) {
+    if (a->dn_bytes == 1 && (p.C == 3 || p.C == 1) && a->algo != 1) {
         const size_t off = tab_smem ? 0 : table_bytes(p.bits, p.C);
         const size_t entries = hot_list_entries((int64_t)p.H * p.W * p.C);
         const size_t list_bytes = ((kHotListHeader + entries) * sizeof(uint32_t) + 15) / 16 * 16;
@@ -713,14 +763,18 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
             p.hot_list = p.bucket_counts + (size_t)p.n_full_tiles * 4;
             p.hot_cap = (uint32_t)entries;
             p.bucket_entries = p.hot_list + list_bytes / sizeof(uint32_t);
-        } else if (a->algo == 2) {
+        } else if ((a->algo == 2 && p.any_dark) || a->algo == 4) {
             return CL_ERR_WORKSPACE;
         }
     }
     int algo = a->algo;
     const bool staged_ok = merge_staged_supported(p, all_std);
     const bool staged_lut_ok = !staged_ok && merge_staged_lut_supported(p);   // no uncertainty images: STD table
-    if (algo == 0) algo = (staged_ok || staged_lut_ok) ? 2 : 1;
+    if (algo == 0) algo = merge_stream_supported(p, all_std) ? 4 : (staged_ok || staged_lut_ok) ? 2 : 1;
+    if (algo == 4) {                   // single-pass kernel (expanded variance, see hdr_merge_stream.cu)
+        if (!merge_stream_supported(p, all_std)) return CL_ERR_UNSUPPORTED;
+        return launch_merge_stream(p, s);
+    }
     if (algo == 2) {
         if (staged_lut_ok) return launch_merge_staged_lut(p, s);
         if (!staged_ok) return CL_ERR_UNSUPPORTED;

@@ -44,7 +44,13 @@ struct MergeParams {
     // exposures whose dark frame can flag a bad pixel (dark[k] set and hot_dn[k] <= max DN), in order
     int32_t n_dark;
     uint8_t dark_k[CL_MAX_EXPOSURES];
+    int32_t stream_mode;       // the single-pass kernel runs: the fix-up pass applies its rule (hdr_merge_stream.cu)
 };
+
+// single-pass kernel: a sample whose expanded variance q kept less than this fraction of its largest term A has
+// cancelled by more than 6 digits and is recomputed with the exact two-pass formula; above it the expansion is within
+// 1.1e-16 / kStreamCancel = 1.1e-10 of the two-pass result
+constexpr double kStreamCancel = 1e-6;
 
 constexpr size_t kHotListHeader = 4;   // uint32 entries reserved in front of the list (counter + pad)
 constexpr int kStagedTilePx = 512;     // pixels per tile of the staged kernel
@@ -82,6 +88,30 @@ __device__ __forceinline__ void merge_accumulate_lut(double w, double p1, double
     const double q = z * y;
     acc_var = fma(q, q, acc_var);
     acc_val = fma(p1, rt, acc_val);
+}
+
+// Single-pass form (hdr_merge_stream.cu): the square expanded so that 1/S is a post-factor,
+//   var = A - 2 B rS + C rS^2,  A = sum (x y)^2,  B = sum (x y)(e y),  C = sum (e y)^2,  x = dw g + w dg,  e = dw w g.
+__device__ __forceinline__ void merge_accumulate_expanded(double w, double p1, double dgl, double kappa, double sigma,
+                                                          double rt, double& S, double& acc_val, double& A, double& B,
+                                                          double& C) {
+    const double a = kappa * p1;        // dw * g
+    const double b = w * dgl;           // w * dICRF
+    const double e = a * w;             // dw * w * g
+    const double x = fma(b, sigma, a);  // dw*g + w*dg
+    const double y = (dgl * sigma) * rt;
+    const double X = x * y, E = e * y;
+    A = fma(X, X, A);
+    B = fma(X, E, B);
+    C = fma(E, E, C);
+    acc_val = fma(p1, rt, acc_val);
+    S += w;
+}
+
+// sum_k ((x - e rS) y)^2 from the expanded sums; rounding can leave a tiny negative where the true value is ~0
+__device__ __forceinline__ double expanded_variance(double A, double B, double C, double rS) {
+    const double q = fma(rS * rS, C, fma(-2.0 * rS, B, A));
+    return q < 0.0 ? 0.0 : q;           // (NaN compares false and is kept)
 }
 
 __device__ __forceinline__ double kappa_of(uint32_t d, double kappa_scale) {
@@ -221,6 +251,8 @@ __device__ __forceinline__ double flat_recip(const void* flat, int flat_bytes, i
 }
 
 int launch_merge_staged(const MergeParams& p, cudaStream_t stream);   // hdr_merge_staged.cu
+int launch_merge_stream(const MergeParams& p, cudaStream_t stream);   // hdr_merge_stream.cu
+bool merge_stream_supported(const MergeParams& p, bool all_std_images);
 int launch_merge_staged_lut(const MergeParams& p, cudaStream_t stream);   // hdr_merge_staged_lut.cu
 bool merge_staged_lut_supported(const MergeParams& p);
 int launch_merge_wide(const MergeParams& p, cudaStream_t stream);     // hdr_merge_wide.cu
@@ -231,5 +263,6 @@ bool merge_staged_supported(const MergeParams& p, bool all_std_images);
 int launch_merge_generic_range(const MergeParams& p, int64_t first_item, cudaStream_t stream);
 int launch_dark_scan(const MergeParams& p, cudaStream_t stream);
 int launch_merge_fixup(const MergeParams& p, cudaStream_t stream);
+int clear_hot_list(const MergeParams& p, cudaStream_t stream);
 
 }  // namespace cl

@@ -112,8 +112,12 @@ typedef struct cl_hdr_merge_args {
     double* out_val;              /* device (H,W,C) f64                                     */
     double* out_std;              /* device (H,W,C) f64                                     */
     int32_t algo;                 /* 0 = auto, 1 = generic register kernel,
-                                     2 = bulk-copy staged kernel (uint8, C = 3),
-                                     3 = fused-table kernel (uint16, N <= 16)                */
+                                     2 = bulk-copy staged two-pass kernel (uint8, C = 3 / 1; with std_lut
+                                         and no uncertainty images: its STD-table variant),
+                                     3 = fused-table kernel (uint16, N <= 16),
+                                     4 = single-pass streaming kernel (uint8, C = 3 / 1, uncertainty
+                                         images, N >= 2; expanded variance, <= 1e-9 from the others) --
+                                         what auto picks whenever it applies                   */
     int32_t reserved;
 } cl_hdr_merge_args;
 
