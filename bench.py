@@ -69,6 +69,11 @@ def config_of(wl, world):
             "parallelism": f"independent stacks x{world}, no collective"}
 
 
+# what cl_hdr_merge runs for an 8-bit RGB stack with float64 uncertainty images (include/camera_linearity.h, `algo`)
+MERGE_KERNEL_OF_ALGO = {0: "merge_stream_kernel (single pass; the default)", 4: "merge_stream_kernel (single pass)",
+                        2: "merge_staged_kernel<16> (two passes over the staged tile)", 1: "merge_generic_kernel"}
+
+
 def std_table(C):
     """Synthetic camera STD table (image_set.py:365-385): shot-noise-like, sigma grows with the signal."""
     x = np.linspace(0, 1, 256)
@@ -500,9 +505,11 @@ def run_ours(args, wl):
         "config": config_of(wl, world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(args.workload) if args.algo != 1 else None, "traffic_source":
-                     "ncu dram__bytes_read+write summed over the kernels of one cl_hdr_merge call (merge_staged 4.21 GB + "
-                     "dark scan / flat ROI / fix-up 0.18 GB), profiles/r02_traffic.json", "peak_source": peak_src, "kernel": ("one step = cl_flat_roi_means + cl_hdr_merge (dark_scan + merge_staged_kernel<16>, ~95% of the time, + merge_fixup); "
-                                "achieved = algorithmic bytes / ms_per_step" if args.algo != 1 else "merge_generic_kernel"),
+                     "ncu dram__bytes_read+write summed over the kernels of one step (merge kernel + dark scan / flat ROI / "
+                     "fix-up), profiles/r02_traffic.json (tools/traffic_from_launches.py)", "peak_source": peak_src,
+                     "kernel": (f"one step = cl_flat_roi_means + cl_hdr_merge (dark_scan + {MERGE_KERNEL_OF_ALGO[args.algo]}, "
+                                "~94% of the time, + merge_fixup); achieved = algorithmic bytes / ms_per_step"
+                                if args.algo != 1 else "merge_generic_kernel"),
                      "algorithmic_bytes_per_launch": alg_bytes, "step_ms_by_per_step_events": kernel_ms},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "Gpix*exposures/s", "h2d_bytes_per_step": world * h2d,
@@ -936,7 +943,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg5"])
-    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 generic kernel, 2 staged kernel")
+    ap.add_argument("--algo", type=int, default=0, choices=[0, 1, 2, 4],
+                    help="0 auto, 1 generic kernel, 2 staged two-pass kernel, 4 single-pass kernel")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -26,6 +26,11 @@
 // (bad pixels: the K x K medians of a tile's bucket from global memory, one or two tiles ahead) and a patcher warp
 // (writes the repaired DN byte and sigma over each stage as it lands and only then declares it ready): 608 threads,
 // 24 shared-memory wavefronts per warp and exposure instead of 32.
+//
+// Ring depth (measured by capping the stage count, cfg2, ms per merge call with / without corrections):
+//   4 stages 0.952 / 0.805,  5: 0.898 / 0.749,  6: 0.856 / 0.726,  7: 0.825 / 0.725  -- i.e. 0.412 us per 13.8 KB stage
+// and SM at the plateau = 5.5 TB/s of reads + writes, where every read-dominated kernel of this library levels off
+// (84 % of the copy bandwidth in MEASURED_PEAKS.json); the corrected path reaches the same per-stage rate at 7.
 #include "staged_common.cuh"
 
 namespace cl {

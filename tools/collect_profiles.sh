@@ -7,7 +7,8 @@ python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $O/r2_plain_bench.jso
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
     --log-file $O/r2_launches_cfg2.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $O/ncu_launches.log 2>&1
 NCU="ncu --set full --clock-control none --import-source on"
-$NCU -k regex:merge_staged_kernel -s 2 -c 1 -o $O/r2_merge_staged python tools/run_merge.py 0.05 3 1 1 > $O/ncu_a.log 2>&1
+$NCU -k regex:merge_stream_kernel -s 2 -c 1 -o $O/r2_merge_stream python tools/run_merge.py 0.05 3 1 1 > $O/ncu_a0.log 2>&1
+$NCU -k regex:merge_staged_kernel -s 2 -c 1 -o $O/r2_merge_staged python tools/run_merge.py 0.05 3 1 1 - 2 > $O/ncu_a.log 2>&1
 $NCU -k regex:merge_staged_lut -s 2 -c 1 -o $O/r2_merge_staged_lut python tools/run_merge.py 0.05 3 1 1 lut > $O/ncu_b.log 2>&1
 $NCU -k regex:dark_scan -s 2 -c 1 -o $O/r2_dark_scan python tools/run_merge.py 0.05 3 1 1 > $O/ncu_c.log 2>&1
 $NCU -k regex:roi_partial -s 1 -c 1 -o $O/r2_roi python tools/run_merge.py 0.05 3 1 1 > $O/ncu_d.log 2>&1

@@ -1,6 +1,7 @@
 """Run ops.hdr_merge on the cfg2 bench stack a few times (profiling target for ncu).
 
-    python tools/run_merge.py [dark_threshold] [reps] [darks:0|1] [flat:0|1] [lut]      (lut: sigma from the STD table)
+    python tools/run_merge.py [dark_threshold] [reps] [darks:0|1] [flat:0|1] [lut|-] [algo]
+    (lut: sigma from the STD table; algo: 0 auto, 1 generic, 2 staged two-pass, 4 single-pass)
 """
 import sys
 from pathlib import Path
@@ -20,6 +21,7 @@ def main():
     use_darks = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
     use_flat = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
     use_lut = len(sys.argv) > 5 and sys.argv[5] == "lut"
+    algo = int(sys.argv[6]) if len(sys.argv) > 6 else 0
     dev = torch.device("cuda:0")
     wl = bench.WORKLOADS["cfg2"]
     data = bench.make_stack_device(wl, 1234, dev)
@@ -37,7 +39,7 @@ def main():
     for r in range(reps):
         out = ops.hdr_merge(data["dn"], None if use_lut else data["std"], t, icrf, diff,
                             std_lut=torch.from_numpy(bench.std_table(3)).to(dev) if use_lut else None,
-                            darks=data["darks"], dark_threshold=thr,
+                            darks=data["darks"], dark_threshold=thr, algo=algo,
                             median_kernel=bench.KERNEL, flat=data["flat"], flat_std=data["flat_std"],
                             flat_means=means)
         ev[r + 1].record()
