@@ -932,6 +932,29 @@ def extra_kernels(dev):
     out["k3_welford_stack"]["cpu_baseline"] = {"value": n_f * 1080 * 1920 / dt / 1e9, "unit": "Gpix*frames/s", "cores": 1,
                                                "kind": "port", "sample": f"{n_f} frames 1080x1920x3, NumPy port of "
                                                                          f"welford_algorithm, {dt:.2f} s"}
+    # K3 end to end through the public call: welford_algorithm over host frames (a frame source standing in for the
+    # OpenCV decoder), i.e. host copy into the pinned staging buffers + H2D on the copy stream + cl_welford_update
+    # per chunk + finalize; the result frames come back to the host.
+    from camera_linearity_b200 import video_processing as vp
+    n_in = 240
+    host_video = frames[:n_in].cpu().numpy()
+
+    def source(_path):
+        for f in host_video:
+            yield f
+    for use_icrf in (False, True):
+        vp.welford_algorithm(Path("synthetic.avi"), icrf_np if use_icrf else None, True, frame_source=source)   # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ret = vp.welford_algorithm(Path("synthetic.avi"), icrf_np if use_icrf else None, True, frame_source=source)
+        ret["mean"].cpu(), ret["sem"].cpu()
+        dt = time.perf_counter() - t0
+        out["k3_welford_stack_icrf" if use_icrf else "k3_welford_stack"]["e2e"] = {
+            "value": n_in * 1080 * 1920 / dt / 1e9, "unit": "Gpix*frames/s", "frames": n_in, "seconds": dt,
+            "h2d_bytes": int(host_video.nbytes), "GB/s_host_to_result": host_video.nbytes / dt / 1e9,
+            "api": "video_processing.welford_algorithm(frame_source=host frames): pinned double-buffered staging, "
+                   "H2D on a copy stream, cl_welford_update per chunk, cl_welford_finalize; bound by the host-side copy "
+                   "of each frame into the staging buffer (one core)"}
     del frames, ws
     return out
 
