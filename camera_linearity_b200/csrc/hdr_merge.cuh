@@ -96,10 +96,10 @@ __device__ __forceinline__ void merge_accumulate_expanded(double w, double p1, d
                                                           double rt, double& S, double& acc_val, double& A, double& B,
                                                           double& C) {
     const double a = kappa * p1;        // dw * g
-    const double b = w * dgl;           // w * dICRF
     const double e = a * w;             // dw * w * g
-    const double x = fma(b, sigma, a);  // dw*g + w*dg
-    const double y = (dgl * sigma) * rt;
+    const double u = dgl * sigma;       // dg
+    const double x = fma(w, u, a);      // dw*g + w*dg
+    const double y = u * rt;
     const double X = x * y, E = e * y;
     A = fma(X, X, A);
     B = fma(X, E, B);

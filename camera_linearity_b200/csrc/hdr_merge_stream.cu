@@ -27,10 +27,19 @@
 // (writes the repaired DN byte and sigma over each stage as it lands and only then declares it ready): 608 threads,
 // 24 shared-memory wavefronts per warp and exposure instead of 32.
 //
-// Ring depth (measured by capping the stage count, cfg2, ms per merge call with / without corrections):
-//   4 stages 0.952 / 0.805,  5: 0.898 / 0.749,  6: 0.856 / 0.726,  7: 0.825 / 0.725  -- i.e. 0.412 us per 13.8 KB stage
-// and SM at the plateau = 5.5 TB/s of reads + writes, where every read-dominated kernel of this library levels off
-// (84 % of the copy bandwidth in MEASURED_PEAKS.json); the corrected path reaches the same per-stage rate at 7.
+// What bounds it (tools/microbench/read_bw.cu: the same ring with the arithmetic removed streams 7.3 TB/s pure read and
+// 6.6 TB/s with this kernel's 24 KB of output per 17 stages at 7 stages x 13.8 KB -- the copy figure in
+// MEASURED_PEAKS.json, 6.56 TB/s, is not the ceiling of a read-dominated stream): the CONSUMERS.  Capping the ring
+// (4 / 5 / 6 / 7 stages: 0.805 / 0.749 / 0.726 / 0.725 ms without corrections) shows the copy side saturating while
+// every instruction taken out of the consumer loop still pays:
+//   * kappa(dn) rides in the weight table ({w, kappa} as a double2, 8 copies, the same 32 KB) instead of being rebuilt
+//     from the DN with an int->double conversion and an FMA per sample-exposure:   0.719 -> 0.685 ms (cfg2, no
+//     corrections), 0.834 -> 0.812 with dark frames + flat;
+//   * x = fma(w, dg, a) with dg = dICRF sigma shared with y = dg / t (12 instead of 13 FP64 operations): 0.685 -> 0.670 ms
+//     = 5.9 TB/s, 91 % of the copy peak.
+// Per pixel-exposure the loop is now ~37 FP64 + ~36 other + ~18 ring-bookkeeping instructions.  With corrections
+// (0.807 ms) the extras are: dark scan 0.039, the flat stage 0.073 (0.034 of traffic + a second epilogue's worth of
+// FP64: ~28 operations and a square root per sample), repairs 0.024 (~11 medians per tile in the bench stack).
 #include "staged_common.cuh"
 
 namespace cl {
@@ -45,7 +54,7 @@ constexpr int kThreads = kTilePx + 96;          // + producer, median and patche
 constexpr int kDnChunk = kTilePx * kC;          // 1536 B
 constexpr int kStdChunk = kTilePx * kC * 8;     // 12288 B
 constexpr int kStage = kStdChunk + kDnChunk;    // 13824 B = 108 x 128
-constexpr int kLutACopies = 16;
+constexpr int kLutACopies = 8;
 constexpr int kLutBCopies = 8;
 constexpr int kMaxStages = 8;
 constexpr size_t kSmemLimit = 227 * 1024;
@@ -80,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 merge_stream_kernel(const __grid_constant__ MergeParams p, const StreamLayout L, const int n_tiles) {
     constexpr int kCt = MONO ? 1 : kC;           // true channel count
     extern __shared__ __align__(128) unsigned char smem[];
-    double* lutA = reinterpret_cast<double*>(smem + L.off_lutA);
+    double2* lutA = reinterpret_cast<double2*>(smem + L.off_lutA);       // [dn][copy] {w, kappa}
     double2* lutB = reinterpret_cast<double2*>(smem + L.off_lutB);
     unsigned char* ring = smem + L.off_ring;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
@@ -117,8 +126,9 @@ merge_stream_kernel(const __grid_constant__ MergeParams p, const StreamLayout L,
             double w, dw;
             gaussian_weight(__ddiv_rn((double)d, p.max_dn), w, dw);
             if (part == 0) {
+                const double2 e = make_double2(w, kappa_of((uint32_t)d, p.kappa_scale));
 #pragma unroll
-                for (int r = 0; r < kLutACopies; ++r) lutA[d * kLutACopies + r] = w;
+                for (int r = 0; r < kLutACopies; ++r) lutA[d * kLutACopies + r] = e;
             } else {
                 const int c = part - 1;
                 const int cs = MONO ? 0 : c;
@@ -218,7 +228,7 @@ merge_stream_kernel(const __grid_constant__ MergeParams p, const StreamLayout L,
     } else {
         // ===== consumers: thread tid owns pixel tid of each tile; ONE pass over the tile's stages =====
         uint64_t* const c_full = patched ? ready : full;
-        const double* myA = lutA + (lane & (kLutACopies - 1));
+        const double2* myA = lutA + (lane & (kLutACopies - 1));
         const double2* myB = lutB + (lane & (kLutBCopies - 1));
         // bytes tid*3 .. tid*3+2 of a DN chunk live in words a_word, a_word+1 (the second word of the last pixel lies
         // just past the chunk: inside the next stage or the barrier block, and contributes only the masked-off top byte)
@@ -241,13 +251,13 @@ merge_stream_kernel(const __grid_constant__ MergeParams p, const StreamLayout L,
                 const uint32_t q = __funnelshift_r(aw[0], aw[1], a_shift) & 0xFFFFFFu;
                 const uint32_t d0 = q & 0xFF, d1 = (q >> 8) & 0xFF, d2 = q >> 16;
                 const double rt = p.inv_t[k];
-                const double w0 = myA[d0 * kLutACopies], w1 = myA[d1 * kLutACopies], w2 = myA[d2 * kLutACopies];
+                const double2 w0 = myA[d0 * kLutACopies], w1 = myA[d1 * kLutACopies], w2 = myA[d2 * kLutACopies];
                 const double2 e0 = myB[(0 * 256 + d0) * kLutBCopies];
                 const double2 e1 = myB[(1 * 256 + d1) * kLutBCopies];
                 const double2 e2 = myB[(2 * 256 + d2) * kLutBCopies];
-                merge_accumulate_expanded(w0, e0.x, e0.y, kappa_of(d0, p.kappa_scale), g0, rt, S0, av0, A0, B0, C0);
-                merge_accumulate_expanded(w1, e1.x, e1.y, kappa_of(d1, p.kappa_scale), g1, rt, S1, av1, A1, B1, C1);
-                merge_accumulate_expanded(w2, e2.x, e2.y, kappa_of(d2, p.kappa_scale), g2, rt, S2, av2, A2, B2, C2);
+                merge_accumulate_expanded(w0.x, e0.x, e0.y, w0.y, g0, rt, S0, av0, A0, B0, C0);
+                merge_accumulate_expanded(w1.x, e1.x, e1.y, w1.y, g1, rt, S1, av1, A1, B1, C1);
+                merge_accumulate_expanded(w2.x, e2.x, e2.y, w2.y, g2, rt, S2, av2, A2, B2, C2);
                 __syncwarp();
                 if (lane == 0 && consumed_nonneg(A0, A1, A2)) mbar_arrive(&empty[s]);
                 if (++s == stages) { s = 0; phase ^= 1; }
@@ -300,7 +310,7 @@ merge_stream_kernel(const __grid_constant__ MergeParams p, const StreamLayout L,
 
 bool make_stream_layout(StreamLayout& L) {
     uint32_t off = 0;
-    L.off_lutA = off; off += 256 * kLutACopies * 8;
+    L.off_lutA = off; off += 256 * kLutACopies * 16;
     L.off_lutB = off; off += kC * 256 * kLutBCopies * 16;
     L.off_ring = off;
     const size_t room = kSmemLimit - 256 - 2 * kBucketCap * sizeof(MedEntry) - off;
