@@ -526,6 +526,7 @@ def run_ours(args, wl):
                     "(image_set.py:228-243, 365-385 -- the reference's path whenever no '... STD.tif' exists)",
             "value": world * pix_exp / (tab_ms * 1e-3) / 1e9, "unit": "Gpix*exposures/s", "ms_per_step": tab_ms,
             "algorithmic_bytes_per_step": alg_bytes - wl["N"] * n_samp * 8,
+            "kernel": "merge_stream_lut_kernel (single pass; tables {w, P1} and {x dg, e dg} in shared memory)",
             "bound": "sm (shared-memory table gathers + FP64), not HBM: "
                      f"{(alg_bytes - wl['N'] * n_samp * 8) / tab_ms / 1e6:.0f} GB/s of algorithmic traffic",
             "e2e": {"value": e2e_tab_value, "unit": "Gpix*exposures/s", "h2d_bytes_per_step": world * h2d_tab,

@@ -387,16 +387,21 @@ __device__ __noinline__ void recompute_sample_stream(const MergeParams& p, int64
     for (int k = 0; k < p.n; ++k) {
         const uint8_t* img = reinterpret_cast<const uint8_t*>(p.dn[k]);
         uint32_t d = img[i];
-        double sg = p.std[k][i];
-        if (p.dark[k] && (uint32_t) reinterpret_cast<const uint8_t*>(p.dark[k])[i] >= p.hot_dn[k]) {
-            d = median_dn(img, y, x, c, p.H, p.W, C, p.K);
-            sg = median_std(p.std[k], img, p.std_lut, y, x, c, p.H, p.W, C, p.K);
-        }
+        const bool hot = p.dark[k] && (uint32_t) reinterpret_cast<const uint8_t*>(p.dark[k])[i] >= p.hot_dn[k];
+        if (hot) d = median_dn(img, y, x, c, p.H, p.W, C, p.K);
+        const double sg = hot ? median_std(p.std[k], img, p.std_lut, y, x, c, p.H, p.W, C, p.K)
+                              : p.std[k] ? p.std[k][i] : p.std_lut[(int64_t)d * C + c];
         double w, dw;
         gaussian_weight(__ddiv_rn((double)d, p.max_dn), w, dw);
         const double p1 = w * p.lut[(int64_t)d * C + c];
-        merge_accumulate_expanded(w, p1, p.dlut[(int64_t)d * C + c], kappa_of(d, p.kappa_scale), sg, p.inv_t[k], S, av,
-                                  A, B, Cc);
+        if (p.stream_mode == 2) {           // the STD-table kernel's arithmetic (products per DN, then 1/t)
+            double xu, eu;
+            lut_products(w, p1, p.dlut[(int64_t)d * C + c], kappa_of(d, p.kappa_scale), sg, xu, eu);
+            merge_accumulate_expanded_lut(w, p1, xu, eu, p.inv_t[k], S, av, A, B, Cc);
+        } else {
+            merge_accumulate_expanded(w, p1, p.dlut[(int64_t)d * C + c], kappa_of(d, p.kappa_scale), sg, p.inv_t[k], S,
+                                      av, A, B, Cc);
+        }
     }
     const double rS = 1.0 / S;
     const double q = expanded_variance(A, B, Cc, rS);
@@ -770,10 +775,13 @@ int cl_hdr_merge(const cl_hdr_merge_args* a, void* workspace, size_t workspace_b
     int algo = a->algo;
     const bool staged_ok = merge_staged_supported(p, all_std);
     const bool staged_lut_ok = !staged_ok && merge_staged_lut_supported(p);   // no uncertainty images: STD table
-    if (algo == 0) algo = merge_stream_supported(p, all_std) ? 4 : (staged_ok || staged_lut_ok) ? 2 : 1;
-    if (algo == 4) {                   // single-pass kernel (expanded variance, see hdr_merge_stream.cu)
-        if (!merge_stream_supported(p, all_std)) return CL_ERR_UNSUPPORTED;
-        return launch_merge_stream(p, s);
+    const bool stream_ok = merge_stream_supported(p, all_std);                // float64 uncertainty images
+    const bool stream_lut_ok = !stream_ok && merge_stream_lut_supported(p);   // STD table
+    if (algo == 0) algo = (stream_ok || stream_lut_ok) ? 4 : (staged_ok || staged_lut_ok) ? 2 : 1;
+    if (algo == 4) {                   // single-pass kernels (expanded variance, see hdr_merge_stream.cu)
+        if (stream_ok) return launch_merge_stream(p, s);
+        if (stream_lut_ok) return launch_merge_stream_lut(p, s);
+        return CL_ERR_UNSUPPORTED;
     }
     if (algo == 2) {
         if (staged_lut_ok) return launch_merge_staged_lut(p, s);

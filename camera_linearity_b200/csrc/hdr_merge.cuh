@@ -44,7 +44,8 @@ struct MergeParams {
     // exposures whose dark frame can flag a bad pixel (dark[k] set and hot_dn[k] <= max DN), in order
     int32_t n_dark;
     uint8_t dark_k[CL_MAX_EXPOSURES];
-    int32_t stream_mode;       // the single-pass kernel runs: the fix-up pass applies its rule (hdr_merge_stream.cu)
+    int32_t stream_mode;       // a single-pass kernel runs and the fix-up pass applies its rule: 1 = uncertainty images
+                               // (hdr_merge_stream.cu), 2 = STD table (hdr_merge_stream_lut.cu)
 };
 
 // single-pass kernel: a sample whose expanded variance q kept less than this fraction of its largest term A has
@@ -101,6 +102,29 @@ __device__ __forceinline__ void merge_accumulate_expanded(double w, double p1, d
     const double x = fma(w, u, a);      // dw*g + w*dg
     const double y = u * rt;
     const double X = x * y, E = e * y;
+    A = fma(X, X, A);
+    B = fma(X, E, B);
+    C = fma(E, E, C);
+    acc_val = fma(p1, rt, acc_val);
+    S += w;
+}
+
+// The single-pass form when sigma comes from the camera's STD table (hdr_merge_stream_lut.cu): x y = (x dg) / t and
+// e y = (e dg) / t, and both products are functions of (dn, c) alone -- tabulated per DN by lut_products(), the
+// exposure contributes two multiplies by 1/t and the five accumulations.
+__device__ __forceinline__ void lut_products(double w, double p1, double dgl, double kappa, double sigma, double& xu,
+                                             double& eu) {
+    const double a = kappa * p1;        // dw * g
+    const double e = a * w;             // dw * w * g
+    const double u = dgl * sigma;       // dg
+    const double x = fma(w, u, a);      // dw*g + w*dg
+    xu = x * u;
+    eu = e * u;
+}
+__device__ __forceinline__ void merge_accumulate_expanded_lut(double w, double p1, double xu, double eu, double rt,
+                                                              double& S, double& acc_val, double& A, double& B,
+                                                              double& C) {
+    const double X = xu * rt, E = eu * rt;
     A = fma(X, X, A);
     B = fma(X, E, B);
     C = fma(E, E, C);
@@ -253,6 +277,8 @@ __device__ __forceinline__ double flat_recip(const void* flat, int flat_bytes, i
 int launch_merge_staged(const MergeParams& p, cudaStream_t stream);   // hdr_merge_staged.cu
 int launch_merge_stream(const MergeParams& p, cudaStream_t stream);   // hdr_merge_stream.cu
 bool merge_stream_supported(const MergeParams& p, bool all_std_images);
+int launch_merge_stream_lut(const MergeParams& p, cudaStream_t stream);   // hdr_merge_stream_lut.cu
+bool merge_stream_lut_supported(const MergeParams& p);
 int launch_merge_staged_lut(const MergeParams& p, cudaStream_t stream);   // hdr_merge_staged_lut.cu
 bool merge_staged_lut_supported(const MergeParams& p);
 int launch_merge_wide(const MergeParams& p, cudaStream_t stream);     // hdr_merge_wide.cu

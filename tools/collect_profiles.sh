@@ -9,7 +9,8 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
 NCU="ncu --set full --clock-control none --import-source on"
 $NCU -k regex:merge_stream_kernel -s 2 -c 1 -o $O/r2_merge_stream python tools/run_merge.py 0.05 3 1 1 > $O/ncu_a0.log 2>&1
 $NCU -k regex:merge_staged_kernel -s 2 -c 1 -o $O/r2_merge_staged python tools/run_merge.py 0.05 3 1 1 - 2 > $O/ncu_a.log 2>&1
-$NCU -k regex:merge_staged_lut -s 2 -c 1 -o $O/r2_merge_staged_lut python tools/run_merge.py 0.05 3 1 1 lut > $O/ncu_b.log 2>&1
+$NCU -k regex:merge_stream_lut -s 2 -c 1 -o $O/r2_merge_stream_lut python tools/run_merge.py 0.05 3 1 1 lut > $O/ncu_b0.log 2>&1
+$NCU -k regex:merge_staged_lut -s 2 -c 1 -o $O/r2_merge_staged_lut python tools/run_merge.py 0.05 3 1 1 lut 2 > $O/ncu_b.log 2>&1
 $NCU -k regex:dark_scan -s 2 -c 1 -o $O/r2_dark_scan python tools/run_merge.py 0.05 3 1 1 > $O/ncu_c.log 2>&1
 $NCU -k regex:roi_partial -s 1 -c 1 -o $O/r2_roi python tools/run_merge.py 0.05 3 1 1 > $O/ncu_d.log 2>&1
 $NCU -k regex:energy_partial -s 3 -c 1 -o $O/r2_k4_nostd python tools/run_k4.py 0 3 > $O/ncu_e.log 2>&1

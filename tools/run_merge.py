@@ -34,11 +34,12 @@ def main():
         data["darks"] = None
     if not use_flat:
         data["flat"] = data["flat_std"] = means = None
+    std_lut = torch.from_numpy(bench.std_table(3)).to(dev) if use_lut else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
     ev[0].record()
     for r in range(reps):
         out = ops.hdr_merge(data["dn"], None if use_lut else data["std"], t, icrf, diff,
-                            std_lut=torch.from_numpy(bench.std_table(3)).to(dev) if use_lut else None,
+                            std_lut=std_lut,
                             darks=data["darks"], dark_threshold=thr, algo=algo,
                             median_kernel=bench.KERNEL, flat=data["flat"], flat_std=data["flat_std"],
                             flat_means=means)
