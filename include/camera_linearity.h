@@ -115,9 +115,10 @@ typedef struct cl_hdr_merge_args {
                                      2 = bulk-copy staged two-pass kernel (uint8, C = 3 / 1; with std_lut
                                          and no uncertainty images: its STD-table variant),
                                      3 = fused-table kernel (uint16, N <= 16),
-                                     4 = single-pass streaming kernel (uint8, C = 3 / 1, uncertainty
-                                         images, N >= 2; expanded variance, <= 1e-9 from the others) --
-                                         what auto picks whenever it applies                   */
+                                     4 = single-pass streaming kernels (uint8, C = 3 / 1, N >= 2, either
+                                         uncertainty images for every exposure or std_lut and none;
+                                         expanded variance, <= 1e-9 from the others) -- what auto picks
+                                         whenever it applies                                   */
     int32_t reserved;
 } cl_hdr_merge_args;
 
