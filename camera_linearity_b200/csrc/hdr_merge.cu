@@ -326,55 +326,6 @@ dark_scan_kernel(const __grid_constant__ MergeParams p) {
     for (uint32_t e = threadIdx.x; e < parked; e += kScanThreads) file_hit(p, (int)hits[e].y, hits[e].x);
 }
 
-// Full recomputation of one sample with the bad-pixel repair, same arithmetic (and the same
-// table values, recomputed on the fly) as the streaming kernels -> bit-identical to inline repair.
-template <typename DN>
-__device__ __noinline__ void recompute_sample(const MergeParams& p, int64_t i) {
-    const int C = p.C;
-    const int c = (int)(i % C);
-    const int64_t px = i / C;
-    const int y = (int)(px / p.W), x = (int)(px - (int64_t)y * p.W);
-    double S = 0.0;
-    uint32_t hot = 0;
-    for (int k = 0; k < p.n; ++k) {
-        const DN* img = reinterpret_cast<const DN*>(p.dn[k]);
-        uint32_t d = img[i];
-        if (p.dark[k] && (uint32_t) reinterpret_cast<const DN*>(p.dark[k])[i] >= p.hot_dn[k]) {
-            d = median_dn(img, y, x, c, p.H, p.W, C, p.K);
-            hot |= 1u << k;
-        }
-        double w, dw;
-        gaussian_weight(__ddiv_rn((double)d, p.max_dn), w, dw);
-        S += w;
-    }
-    const double rS = 1.0 / S;
-    double av = 0.0, as = 0.0;
-    for (int k = 0; k < p.n; ++k) {
-        const DN* img = reinterpret_cast<const DN*>(p.dn[k]);
-        uint32_t d = img[i];
-        double sg;
-        if (hot & (1u << k)) {
-            d = median_dn(img, y, x, c, p.H, p.W, C, p.K);
-            sg = median_std(p.std[k], img, p.std_lut, y, x, c, p.H, p.W, C, p.K);
-        } else {
-            sg = p.std[k] ? p.std[k][i] : p.std_lut[(int64_t)d * C + c];
-        }
-        double w, dw;
-        gaussian_weight(__ddiv_rn((double)d, p.max_dn), w, dw);
-        const double p1 = w * p.lut[(int64_t)d * C + c];
-        merge_accumulate(w, p1, p.dlut[(int64_t)d * C + c], kappa_of(d, p.kappa_scale), sg, rS, p.inv_t[k],
-                         av, as);
-    }
-    double ov = av * rS, os;
-    if (p.flat_bytes)
-        flat_apply(ov, os, (as * rS) * rS, flat_recip(p.flat, p.flat_bytes, i, p.max_dn), p.flat_std[i],
-                   p.flat_means[c], p.flat_means[C + c]);
-    else
-        os = sqrt(as) * rS;
-    p.out_val[i] = ov;
-    p.out_std[i] = os;
-}
-
 // The single-pass kernel's rule for one sample (hdr_merge_stream.cu): the expanded variance, unless it cancelled
 // (q < kStreamCancel * A), in which case the exact two-pass formula.  Same operations in the same order as the
 // kernel, so a sample gets the same bits whichever of the two computes it.
