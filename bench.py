@@ -621,9 +621,9 @@ def cfg5_measure(dev, rank, world, steps, warmup, std_table=False):
             "algorithmic_bytes_per_stack": alg_stack,
             "achieved_GB/s_per_gpu": alg_stack / (ms_step / per_rank) / 1e6,
             "frac_of_hbm_peak": alg_stack / (ms_step / per_rank) / 1e6 / peak,
-            "bound": "L2 gather throughput: one divergent 16-byte (32-byte with the STD table) table gather per "
-                     "sample-exposure from a 1 MB (2 MB) table; tools/microbench/gather_bench.cu measures the chip's "
-                     "random-gather rate, see DESIGN.md"}
+            "bound": "L1 data pipe: one divergent 16-byte (32-byte with the STD table) table gather per sample-exposure "
+                     "from a 1 MB (2 MB) table = one L1 wavefront per row, 1 per SM clock "
+                     "(tools/microbench/gather_mix.cu; ncu: pipe 84 % busy), see DESIGN.md"}
 
 
 def run_cfg5(args):
