@@ -115,7 +115,7 @@ typedef struct cl_hdr_merge_args {
                                      2 = bulk-copy staged two-pass kernel (uint8, C = 3 / 1; with std_lut
                                          and no uncertainty images: its STD-table variant),
                                      3 = fused-table kernel (uint16, N <= 16; software-pipelined; weights from a
-                                         table-driven exp: <= 1e-13 from the generic kernel, measured 8.5e-16) --
+                                         table-free exp: <= 1e-13 from the generic kernel, measured 6.5e-16) --
                                          what auto picks for uint16 stacks,
                                      4 = single-pass streaming kernels (uint8, C = 3 / 1, N >= 2, either
                                          uncertainty images for every exposure or std_lut and none;
