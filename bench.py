@@ -570,7 +570,7 @@ def cfg5_stack_device(seed, dev, with_std=True):
     return dn, std, t
 
 
-def cfg5_measure(dev, rank, world, steps, warmup, std_table=False):
+def cfg5_measure(dev, rank, world, steps, warmup, std_table=False, sample_clocks=True):
     """The sharded batch of BASELINE config 5: 64 stacks split over the ranks (8 per GPU at N = 8), no collective.
     Each rank keeps min(64 / world, 8) DISTINCT stacks resident (8 stacks = 36 GB) and merges its 64 / world stacks per
     step by cycling over them, so every merge reads data far larger than L2.  Strong scaling: the batch is fixed."""
@@ -596,6 +596,9 @@ def cfg5_measure(dev, rank, world, steps, warmup, std_table=False):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler = ClockSampler(dev) if (rank == 0 and sample_clocks) else None
+    if sampler:
+        sampler.start()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(steps):
@@ -604,6 +607,7 @@ def cfg5_measure(dev, rank, world, steps, warmup, std_table=False):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    block_clocks = sampler.stop() if sampler else None
     tm = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -621,6 +625,9 @@ def cfg5_measure(dev, rank, world, steps, warmup, std_table=False):
             "algorithmic_bytes_per_stack": alg_stack,
             "achieved_GB/s_per_gpu": alg_stack / (ms_step / per_rank) / 1e6,
             "frac_of_hbm_peak": alg_stack / (ms_step / per_rank) / 1e6 / peak,
+            # this block keeps the GPU busy for hundreds of ms: the float64-image variant draws enough power for the
+            # box's software power cap to lower the SM clock (one stack timed alone: 1.48 ms, tools/cfg5_sustained.py)
+            "clocks": block_clocks,
             "bound": "L1 data pipe: one divergent 16-byte (32-byte with the STD table) table gather per sample-exposure "
                      "from a 1 MB (2 MB) table = one L1 wavefront per row, 1 per SM clock "
                      "(tools/microbench/gather_mix.cu; ncu: pipe 84 % busy), see DESIGN.md"}
