@@ -114,9 +114,8 @@ typedef struct cl_hdr_merge_args {
     int32_t algo;                 /* 0 = auto, 1 = generic register kernel,
                                      2 = bulk-copy staged two-pass kernel (uint8, C = 3 / 1; with std_lut
                                          and no uncertainty images: its STD-table variant),
-                                     3 = fused-table kernel (uint16, N <= 16; software-pipelined; weights from a
-                                         table-free exp: <= 1e-13 from the generic kernel, measured 6.5e-16) --
-                                         what auto picks for uint16 stacks,
+                                     3 = fused-table kernel (uint16, N <= 16; software-pipelined, bit-identical to the
+                                         generic kernel) -- what auto picks for uint16 stacks,
                                      4 = single-pass streaming kernels (uint8, C = 3 / 1, N >= 2, either
                                          uncertainty images for every exposure or std_lut and none;
                                          expanded variance, <= 1e-9 from the others) -- what auto picks
