@@ -17,6 +17,8 @@
 // standard errors of the mean the expansion loses nothing (round 1 made a second pass over the inputs, 64 B
 // per sample, only to centre the variance).  Block partials are combined in a fixed order (deterministic); the
 // reference's pairwise summation differs at the 1e-13 level.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace cl {
@@ -134,6 +136,108 @@ __device__ __forceinline__ void accumulate_shifted(double (&acc)[kQ], const Diff
     if (!bad_r && not_nan(tr)) { acc[11] += wr; acc[12] = fma(wr, dr, acc[12]); acc[13] += tr; }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Lean per-sample routine (both uncertainty images present).  The general routine above spends ~210
+// instructions per sample, two thirds of them on bookkeeping: every one of the 14 sums carries its own "is this
+// term NaN" predicate (a compare and two selects each) because np.nansum skips terms individually.  But a sample
+// is almost always in one of two states: ORDINARY (nothing thresholded, nothing NaN, every term finite) -- all
+// 14 terms count -- or DROPPED (value and uncertainty of one side thresholded: every term is skipped).  So:
+//   * the arithmetic runs once, without per-term checks (dropped samples compute on 1.0 so it stays finite);
+//   * ONE predicate zeroes the sample's four weights / uncertainties and its count (9 selects), and the 14 sums
+//     are updated unconditionally -- a dropped sample adds exact zeros;
+//   * a sample in any other state (a NaN in only the value or only the uncertainty image, a zero / denormal /
+//     infinite variance, an infinite ratio) adds zeros here and goes through the general routine instead.
+// Ordinary samples execute the same operations in the same order as the general routine: the statistics are
+// bit-identical to the all-general kernel (CL_PAIR_GENERAL_ONLY builds it for the A/B).
+__device__ __forceinline__ bool normal_positive(double q) {        // finite, >= 2^-1022: rsqrt's own fast-path test
+    return (uint32_t)(__double2hiint(q) - 0x00100000) < 0x7fe00000u;
+}
+
+// The main paths of CUDA's rsqrt() and __drcp_rn(), operation for operation (read off their SASS: MUFU seed, then
+// the same FMA chain), WITHOUT the range checks and slow-path calls: straight-line code, so the four samples a
+// thread has in flight interleave.  Valid -- and bit-identical to the library functions -- where those take
+// their main path: q normal and positive; `ok` = the library's own exponent test on s.  Anything else makes the
+// sample non-ordinary and the general routine (which calls the library functions) counts it.
+__device__ __forceinline__ double rsqrt_main_path(double q) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(q));
+    const double e = __fma_rn(q, -__dmul_rn(y0, y0), 1.0);
+    const double c = __fma_rn(e, 0.375, 0.5);
+    return __fma_rn(c, __dmul_rn(y0, e), y0);
+}
+__device__ __forceinline__ double rcp_main_path(double s, bool& ok) {
+    double seed;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(s));
+    const int lo = __double2hiint(s) + 0x300402;                   // (the library seeds the low word with this)
+    ok = fabsf(__int_as_float(lo)) >= 5.8789094863358348022e-39f;
+    const double y0 = __hiloint2double(__double2hiint(seed), lo);
+    double e = __fma_rn(-s, y0, 1.0);
+    e = __fma_rn(e, e, e);
+    const double y1 = __fma_rn(y0, e, y0);
+    const double e1 = __fma_rn(-s, y1, 1.0);
+    return __fma_rn(y1, e1, y1);
+}
+
+__device__ __forceinline__ bool lean_sample(const PairArgs& p, const Raw& raw, double lo, double hi, double ka,
+                                            double kr, double (&acc)[kQ]) {
+    double x = raw.x, y = raw.y, xs = raw.xs, ys = raw.ys;
+    const bool tx = p.has_thr && (x < lo || x > hi), ty = p.has_thr && (y < lo || y > hi);
+    const bool bad_v = tx || ty || x != x || y != y;               // the reference's value is NaN
+    const bool bad_s = tx || ty || xs != xs || ys != ys;           // ... its uncertainty is NaN
+    const bool any_bad = bad_v || bad_s;
+    x = any_bad ? 1.0 : x;  y = any_bad ? 1.0 : y;  xs = any_bad ? 1.0 : xs;  ys = any_bad ? 1.0 : ys;
+    const double scale = __dmul_rn(p.multiplier, y);
+    bool rcp_ok;
+    const double inv = rcp_main_path(scale, rcp_ok);
+    double a = __dsub_rn(x, scale);
+    double r = __dmul_rn(a, inv);
+    const double my = __dmul_rn(p.multiplier, ys);
+    const double qa = __dadd_rn(__dmul_rn(xs, xs), __dmul_rn(my, my));
+    double wa = rsqrt_main_path(qa);
+    double sa = __dmul_rn(qa, wa);
+    const double t1 = __dmul_rn(xs, inv);
+    const double t2 = __dmul_rn(__dmul_rn(__dmul_rn(ys, x), inv), __dmul_rn(inv, p.multiplier));
+    const double qr = __dadd_rn(__dmul_rn(t1, t1), __dmul_rn(t2, t2));
+    double wr = rsqrt_main_path(qr);
+    double sr = __dmul_rn(qr, wr);
+    const bool ordinary = !any_bad && rcp_ok && normal_positive(qa) && normal_positive(qr) &&
+                          fabs(r) < __longlong_as_double(0x7ff0000000000000LL);
+    const bool dropped = bad_v && bad_s;
+    // everything a non-ordinary sample computed may be garbage (NaN, inf): selects, not multiplications by zero
+    a = ordinary ? a : 0.0;    r = ordinary ? r : 0.0;
+    wa = ordinary ? wa : 0.0;  wr = ordinary ? wr : 0.0;
+    sa = ordinary ? sa : 0.0;  sr = ordinary ? sr : 0.0;
+    const double one = ordinary ? 1.0 : 0.0;
+    const double da = __dsub_rn(a, ka), dr = __dsub_rn(r, kr);
+    acc[0] += wa;
+    acc[1] += __dmul_rn(a, wa);
+    acc[2] += sa;
+    acc[3] += one;
+    acc[4] += wr;
+    acc[5] += __dmul_rn(r, wr);
+    acc[6] += sr;
+    acc[7] += one;
+    acc[8] += wa;
+    acc[9] = fma(wa, da, acc[9]);
+    acc[10] += __dmul_rn(wa, __dmul_rn(da, da));
+    acc[11] += wr;
+    acc[12] = fma(wr, dr, acc[12]);
+    acc[13] += __dmul_rn(wr, __dmul_rn(dr, dr));
+    return !(ordinary || dropped);                                 // true: the general routine must count this sample
+}
+
+template <bool USE_STD, bool LEAN>
+__device__ __forceinline__ void count_sample(const PairArgs& p, const Raw& raw, double lo, double hi, double ka,
+                                             double kr, double (&acc)[kQ]) {
+    if (LEAN) {
+        if (!lean_sample(p, raw, lo, hi, ka, kr, acc)) return;
+    }
+    const Diff d = difference(p, raw, lo, hi, USE_STD);
+    double (&a8)[8] = reinterpret_cast<double (&)[8]>(acc);
+    accumulate1<USE_STD>(a8, d);
+    accumulate_shifted<USE_STD>(acc, d, ka, kr);
+}
+
 // Deterministic block reduction of per-thread accumulators: thread t owns channel (t % C) because
 // the grid stride is a multiple of C.  acc -> shared [Q][kThreads]; then Q*C threads sum their
 // column in index order.
@@ -159,7 +263,7 @@ __device__ __forceinline__ double kr_of(const double (&shift)[4][CL_MAX_CHANNELS
     return shift[3][c] > 0.0 ? shift[2][c] / shift[3][c] : 0.0;
 }
 
-template <bool USE_STD>
+template <bool USE_STD, bool LEAN>
 __global__ void __launch_bounds__(kThreads, 2)
 pair_stats_kernel(const PairArgs p, double* __restrict__ partial /* [blocks][kQ][C] */) {
     const int C = p.C;
@@ -206,19 +310,9 @@ pair_stats_kernel(const PairArgs p, double* __restrict__ partial /* [blocks][kQ]
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) raw[u] = load_raw(p, i + u * stride);
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const Diff d = difference(p, raw[u], lo, hi, USE_STD);
-                double (&a8)[8] = reinterpret_cast<double (&)[8]>(acc);
-                accumulate1<USE_STD>(a8, d);
-                accumulate_shifted<USE_STD>(acc, d, ka, kr);
-            }
+            for (int u = 0; u < kUnroll; ++u) count_sample<USE_STD, LEAN>(p, raw[u], lo, hi, ka, kr, acc);
         }
-        for (; i < p.n; i += stride) {
-            const Diff d = difference(p, load_raw(p, i), lo, hi, USE_STD);
-            double (&a8)[8] = reinterpret_cast<double (&)[8]>(acc);
-            accumulate1<USE_STD>(a8, d);
-            accumulate_shifted<USE_STD>(acc, d, ka, kr);
-        }
+        for (; i < p.n; i += stride) count_sample<USE_STD, LEAN>(p, load_raw(p, i), lo, hi, ka, kr, acc);
     }
     block_reduce<kQ>(acc, C, lanes_used, partial + (int64_t)blockIdx.x * kQ * C);
     if (blockIdx.x == 0 && threadIdx.x < 2 * C)              // the shifts, for the final kernel
@@ -257,6 +351,10 @@ __global__ void pair_final_kernel(const double* __restrict__ partial, int n_bloc
     const double dm = mean - K;
     double q = fma(dm * dm, T0, fma(-2.0 * dm, T1, T2));                      // sum w (v - mean)^2
     if (q < 0.0) q = 0.0;
+    // degenerate means, as np.nansum sees them: (v - NaN)^2 is NaN for every sample -> an empty sum; (v - inf)^2 is
+    // inf for every finite v
+    if (mean != mean) q = 0.0;
+    else if (fabs(mean) == __longlong_as_double(0x7ff0000000000000LL)) q = T0 > 0.0 ? fabs(mean) : 0.0;
     stats[(which * 3 + 0) * C + c] = mean;
     stats[(which * 3 + 1) * C + c] = sqrt(q / denom);
     stats[(which * 3 + 2) * C + c] = use_std ? totals[(which * 4 + 2) * C + c] / totals[(which * 4 + 3) * C + c]
@@ -293,8 +391,14 @@ int cl_pair_statistics(const double* x_val, const double* x_std, const double* y
     const bool use_std = x_std != nullptr || y_std != nullptr;
     cudaStream_t s = (cudaStream_t)stream;
     double* partial = reinterpret_cast<double*>(workspace);
-    if (use_std) pair_stats_kernel<true><<<kBlocks, kThreads, 0, s>>>(p, partial);
-    else pair_stats_kernel<false><<<kBlocks, kThreads, 0, s>>>(p, partial);
+    // the lean routine needs both uncertainty images and a multiplier whose products stay finite on 1.0
+    bool lean = x_std && y_std && multiplier == multiplier && fabs(multiplier) >= 1e-100 && fabs(multiplier) <= 1e100;
+#ifdef CL_PAIR_GENERAL_ONLY
+    lean = false;
+#endif
+    if (lean) pair_stats_kernel<true, true><<<kBlocks, kThreads, 0, s>>>(p, partial);
+    else if (use_std) pair_stats_kernel<true, false><<<kBlocks, kThreads, 0, s>>>(p, partial);
+    else pair_stats_kernel<false, false><<<kBlocks, kThreads, 0, s>>>(p, partial);
     int st = launched();
     if (st != CL_OK) return st;
     pair_final_kernel<<<1, 1024, 0, s>>>(partial, kBlocks, channels, use_std ? 1 : 0, stats);

@@ -96,3 +96,62 @@ def test_exposure_series_process_linearity_uses_the_fused_path():
             assert_rel(relative["stds"][k], r["std"], TIGHT)
             assert_rel(absolute["errors"][k], a["error"], TIGHT)
             k += 1
+
+
+@pytest.mark.parametrize("shape", [(701, 503, 3), (611, 517, 1), (400, 333, 4)])
+def test_large_pairs_with_special_samples_against_the_oracle(shape):
+    """Many grid-stride rounds per thread (the golden pair is small): NaN / zero-scale / thresholded samples at regular
+    strides and in the ragged tail, repeat-identical, and the same data at an odd element offset (mono)."""
+    rng = np.random.default_rng(shape[0])
+    n = int(np.prod(shape))
+    x, y = rng.random(shape) + 0.05, rng.random(shape) + 0.05
+    xs, ys = rng.uniform(0.001, 0.02, shape), rng.uniform(0.001, 0.02, shape)
+    fx, fy, fxs, fys = (a.reshape(-1) for a in (x, y, xs, ys))
+    c = shape[-1]
+    tile = (256 // c) * c * 2
+    spots = np.concatenate([np.arange(0, n, tile)[:200], np.arange(tile - 1, n, tile)[:200], np.arange(n - 7, n)])
+    fx[spots[0::5]] = np.nan
+    fy[spots[1::5]] = np.nan
+    fys[spots[2::5]] = np.nan
+    fxs[spots[3::5]] = np.nan
+    fy[spots[4::5]] = 0.0                        # scale == 0 -> inf / NaN relative difference
+    lower, upper = [0.1] * c, [0.9 - 0.01 * i for i in range(c)]
+    a, r = oli.pair_statistics(x, xs, y, ys, 0.41, lower, upper)
+    first = ops.pair_statistics(dev(x), dev(xs), dev(y), dev(ys), 0.41, lower, upper)
+    _check(first, a, r, True)
+    assert torch.equal(first, ops.pair_statistics(dev(x), dev(xs), dev(y), dev(ys), 0.41, lower, upper))
+
+    def odd(arr):                                # same values, pointer = 8 mod 16
+        buf = torch.empty(n + c, dtype=torch.float64, device="cuda")
+        view = buf[1:n + 1].view(shape) if c == 1 else None
+        if view is None:                         # keep the channel phase: shift by one element only works for C == 1
+            return None
+        view.copy_(dev(arr))
+        return view
+    if c == 1:
+        direct = ops.pair_statistics(odd(x), odd(xs), odd(y), odd(ys), 0.41, lower, upper)
+        np.testing.assert_allclose(host(direct), host(first), rtol=1e-12, equal_nan=True)
+
+
+def test_samples_that_are_neither_ordinary_nor_dropped():
+    """No thresholds, so nothing is dropped wholesale: a zero scale (infinite ratio), zero variances (infinite weights),
+    infinities and NaNs in only the value or only the uncertainty image must be counted term by term exactly as
+    np.nansum does -- the lean per-sample routine hands them to the general one."""
+    rng = np.random.default_rng(77)
+    shape = (300, 257, 4)
+    x, y = rng.random(shape) + 0.05, rng.random(shape) + 0.05
+    xs, ys = rng.uniform(0.001, 0.02, shape), rng.uniform(0.001, 0.02, shape)
+    x[5::41, 3::7, 0] = np.nan                   # value NaN, uncertainty kept
+    xs[7::43, 1::5, 0] = np.nan                  # uncertainty NaN, value kept
+    y[3::37, 2::9, 1] = 0.0                      # scale == 0: relative difference +-inf, its uncertainty inf
+    xs[2::31, 4::11, 2] = 0.0
+    ys[2::31, 4::11, 2] = 0.0                    # zero variance: infinite weight
+    x[11::47, 5::13, 3] = np.inf
+    ys[13::53, 6::17, 3] = 1e-170                # variance underflows to a denormal
+    with np.errstate(all="ignore"):
+        a, r = oli.pair_statistics(x, xs, y, ys, 0.8)
+    s = host(ops.pair_statistics(dev(x), dev(xs), dev(y), dev(ys), 0.8))
+    for which, st in ((0, a), (1, r)):
+        for k, name in enumerate(("mean", "std", "error")):
+            np.testing.assert_allclose(s[which, k], st[name], rtol=1e-10, equal_nan=True, err_msg=f"{which} {name}")
+    assert np.isfinite(s[:, :, :2]).any()        # the case is not all-NaN
