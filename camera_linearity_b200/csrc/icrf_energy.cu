@@ -161,7 +161,7 @@ __device__ __forceinline__ void load_pixel(PixelData<N, USE_STD>& d, const uint8
 
 // UNIFORM (lower >= 1): `vmask` bit k = exposure k of this pixel is inside [lower, upper] (warp-uniform)
 template <int N, bool USE_STD, int P>
-__device__ __forceinline__ void accumulate_pixel_uniform(const PixelData<N, USE_STD>& d, uint32_t vmask,
+__device__ __forceinline__ uint32_t accumulate_pixel_uniform(const PixelData<N, USE_STD>& d, uint32_t vmask,
                                                          const double* __restrict__ tabI,
                                                          const double* __restrict__ tabR, int lane,
                                                          const ExposureScales& sc, double (&num)[P], double (&den)[P]) {
@@ -177,6 +177,7 @@ __device__ __forceinline__ void accumulate_pixel_uniform(const PixelData<N, USE_
         if (USE_STD && k < N - 1) C[USE_STD ? k : 0] = d.sg[USE_STD ? k : 0] * sc.inv_t[k];
     }
     int q = 0;
+    uint32_t odd = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
 #pragma unroll
@@ -189,13 +190,53 @@ __device__ __forceinline__ void accumulate_pixel_uniform(const PixelData<N, USE_
                 const double t1 = C[USE_STD ? i : 0] * B[j];
                 const double t2 = u * Dj[USE_STD ? j : 0];
                 const double var = fma(t1, t1, t2 * t2);
-                // pair inside the range (warp-uniform bit) and sigma != 0 (:134); |d| is finite here
-                const bool ok = ((vmask >> i) & (vmask >> j) & 1u) && var > 0.0;
-                const double w = rsqrt(ok ? var : 1.0);
-                if (ok) {
-                    num[q] = fma(a, w, num[q]);
-                    den[q] += w;
-                }
+                // pair inside the range (warp-uniform bit) and sigma != 0 (:134); |d| is finite here.  The weight is
+                // the main path of rsqrt() without its range test and slow-path branch: ten of those per pixel
+                // fenced the schedule (0.375 -> 0.333 ms per population without them; a rare-case branch per PAIR
+                // was slower than the library call, 0.401; one per PIXEL 0.361).  A pair that is out of range or whose
+                // variance is not a normal positive number gets weight 0 and adds exact zeros; the caller notes it
+                // and revisits its pixels after the loop (fix_pixel_uniform).
+                const bool in_range = (vmask >> i) & (vmask >> j) & 1u;
+                const bool fast = in_range && normal_positive(var);
+                double w = rsqrt_main_path(var);
+                w = fast ? w : 0.0;
+                odd |= (uint32_t)(in_range && !fast);
+                num[q] = fma(a, w, num[q]);
+                den[q] += w;
+            }
+        }
+    }
+    return odd;
+}
+
+// Second visit of a pixel that had a pair inside the range whose variance is not a normal positive number: zero / NaN
+// (the pair is skipped, :134) or denormal (library rsqrt).  Only those pairs add something here.
+template <int N, int P>
+__device__ __forceinline__ void fix_pixel_uniform(const PixelData<N, true>& d, uint32_t vmask,
+                                                  const double* __restrict__ tabI, const double* __restrict__ tabR,
+                                                  int lane, const ExposureScales& sc, double (&num)[P], double (&den)[P]) {
+    double A2[N], B2[N], C2[N], D2[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        A2[k] = tabI[d.bin[k] * kGroup + lane] * sc.inv_t[k];
+        const double r = tabR[d.bin[k] * kGroup + lane];
+        B2[k] = r * sc.t[k];
+        D2[k] = d.sg[k] * r;
+        C2[k] = d.sg[k] * sc.inv_t[k];
+    }
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = i + 1; j < N; ++j, ++q) {
+            const double u = A2[i] * B2[j];
+            const double t1 = C2[i] * B2[j];
+            const double t2 = u * D2[j];
+            const double var = fma(t1, t1, t2 * t2);
+            if (((vmask >> i) & (vmask >> j) & 1u) && !normal_positive(var) && var > 0.0) {
+                const double w = rsqrt(var);
+                num[q] = fma(fabs(u - 1.0), w, num[q]);
+                den[q] += w;
             }
         }
     }
@@ -335,13 +376,25 @@ energy_partial_kernel(const double* __restrict__ tables, int D, int S, const uin
         // two pixels per iteration (px and px + WARPS): two independent gather -> multiply -> FMA -> add chains in
         // flight per warp -- with 4 warps per scheduler one chain left the issue slots ~25 % empty
         if (USE_STD) {                  // FP64 bound: one pixel per iteration (the second window only costs registers)
+            uint32_t odd = 0;
             for (; px < last; px += WARPS) {
                 if (px + WARPS < last) load_pixel<N, USE_STD>(nxt, dn, sd, px + WARPS, D);     // prefetch
                 uint32_t vmask = 0;
 #pragma unroll
                 for (int k = 0; k < N; ++k) vmask |= ((uint32_t)(cur.bin[k] - lower) <= span ? 1u : 0u) << k;
-                accumulate_pixel_uniform<N, USE_STD, P>(cur, vmask, tabI, tabR, lane, sc, num, den);
+                odd |= accumulate_pixel_uniform<N, USE_STD, P>(cur, vmask, tabI, tabR, lane, sc, num, den);
                 cur = nxt;
+            }
+            if constexpr (USE_STD) {
+                if (odd) {              // rare: some pair had a zero / NaN / denormal variance -- walk the pixels again
+                    for (px = first + warp; px < last; px += WARPS) {
+                        load_pixel<N, USE_STD>(cur, dn, sd, px, D);
+                        uint32_t vmask = 0;
+#pragma unroll
+                        for (int k = 0; k < N; ++k) vmask |= ((uint32_t)(cur.bin[k] - lower) <= span ? 1u : 0u) << k;
+                        fix_pixel_uniform<N, P>(cur, vmask, tabI, tabR, lane, sc, num, den);
+                    }
+                }
             }
         }
         PixelData<N, USE_STD> cur2, nxt2;

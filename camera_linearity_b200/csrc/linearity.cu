@@ -149,35 +149,7 @@ __device__ __forceinline__ void accumulate_shifted(double (&acc)[kQ], const Diff
 //     infinite variance, an infinite ratio) adds zeros here and goes through the general routine instead.
 // Ordinary samples execute the same operations in the same order as the general routine: the statistics are
 // bit-identical to the all-general kernel (CL_PAIR_GENERAL_ONLY builds it for the A/B).
-__device__ __forceinline__ bool normal_positive(double q) {        // finite, >= 2^-1022: rsqrt's own fast-path test
-    return (uint32_t)(__double2hiint(q) - 0x00100000) < 0x7fe00000u;
-}
-
-// The main paths of CUDA's rsqrt() and __drcp_rn(), operation for operation (read off their SASS: MUFU seed, then
-// the same FMA chain), WITHOUT the range checks and slow-path calls: straight-line code, so the four samples a
-// thread has in flight interleave.  Valid -- and bit-identical to the library functions -- where those take
-// their main path: q normal and positive; `ok` = the library's own exponent test on s.  Anything else makes the
-// sample non-ordinary and the general routine (which calls the library functions) counts it.
-__device__ __forceinline__ double rsqrt_main_path(double q) {
-    double y0;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(q));
-    const double e = __fma_rn(q, -__dmul_rn(y0, y0), 1.0);
-    const double c = __fma_rn(e, 0.375, 0.5);
-    return __fma_rn(c, __dmul_rn(y0, e), y0);
-}
-__device__ __forceinline__ double rcp_main_path(double s, bool& ok) {
-    double seed;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(s));
-    const int lo = __double2hiint(s) + 0x300402;                   // (the library seeds the low word with this)
-    ok = fabsf(__int_as_float(lo)) >= 5.8789094863358348022e-39f;
-    const double y0 = __hiloint2double(__double2hiint(seed), lo);
-    double e = __fma_rn(-s, y0, 1.0);
-    e = __fma_rn(e, e, e);
-    const double y1 = __fma_rn(y0, e, y0);
-    const double e1 = __fma_rn(-s, y1, 1.0);
-    return __fma_rn(y1, e1, y1);
-}
-
+// (normal_positive, rsqrt_main_path, rcp_main_path: common.cuh)
 __device__ __forceinline__ bool lean_sample(const PairArgs& p, const Raw& raw, double lo, double hi, double ka,
                                             double kr, double (&acc)[kQ]) {
     double x = raw.x, y = raw.y, xs = raw.xs, ys = raw.ys;

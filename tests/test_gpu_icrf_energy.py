@@ -86,6 +86,30 @@ def test_exposure_counts_and_population_sizes(n_exp, use_std):
     assert_rel(e, oe.energy_population(params, mean, q, dn, sd, 5, 250, True, t), TIGHT)
 
 
+def test_zero_nan_and_denormal_variances_take_the_exact_branch():
+    """The weighted pixel loop uses rsqrt's main path and revisits a pixel whose pair variance is not a normal
+    positive number: sigma == 0 on both sides (pair skipped, general_functions.py:165-170), sigmas so small that
+    the variance is denormal (library rsqrt), next to ordinary pixels."""
+    rng = np.random.default_rng(11)
+    x = np.linspace(0, 1, 256)
+    mean = x ** 2.0
+    q, _ = np.linalg.qr(np.stack([np.sin((k + 1) * np.pi * x) * x for k in range(5)], axis=1))
+    t = 0.004 * 1.9 ** np.arange(5)
+    rad = rng.uniform(0, 1, (64, 48, 1)) * 30
+    dn = np.rint(255 * np.clip(rad * t[None, None, :], 0, 1) ** 0.5).astype(np.uint8)
+    sd = rng.uniform(0.002, 0.02, dn.shape)
+    sd[::7, ::5, :] = 0.0                        # every pair of the pixel has zero variance
+    sd[1::7, ::5, 1:3] = 0.0                     # some pairs do
+    sd[2::7, 1::5, :] = 2e-155                   # variances around 1e-309 .. 1e-306: denormal (~49 bits) and just normal
+    sd[3::7, 2::5, 0] = 5e-155
+    params = rng.uniform(-0.04, 0.04, (5, 37))
+    with np.errstate(all="ignore"):
+        want = oe.energy_population(params, mean, q, dn, sd, 5, 250, True, t)
+    got = cl.EnergyEvaluator(mean, q, dn, sd, 5, 250, True, t, 37)(params)
+    assert np.isfinite(want).any()
+    assert_rel(got, want, 1e-9)                  # (the denormal weights are ~1e150: their sums lose a few digits)
+
+
 def test_error_contract():
     x = np.linspace(0, 1, 256)
     pca = np.zeros((256, 5))

@@ -55,6 +55,15 @@ def test_adversarial_all_ties():
     o = ow.welford(list(frames))
     _, _, mean_u8 = ops.welford_stack(dev(frames))
     assert np.array_equal(host(mean_u8), o["mean_u8"])
+    # 960 ties: the replay runs one LANE per tie (one warp per tie below 256).  The same through the ICRF path with
+    # the identity table d / 255, whose near-tie samples are replayed from the table in shared memory.
+    ident = np.repeat((np.arange(256) / 255.0)[:, None], 3, axis=1)
+    oi = ow.welford(list(frames), icrf=ident)
+    _, _, mean_u8_i = ops.welford_stack(dev(frames), dev(ident))
+    assert np.array_equal(host(mean_u8_i), oi["mean_u8"])
+    few = frames[:, :4, :5]                          # 60 ties: one warp per tie
+    _, _, mean_u8_f = ops.welford_stack(dev(np.ascontiguousarray(few)))
+    assert np.array_equal(host(mean_u8_f), ow.welford(list(few))["mean_u8"])
 
 
 def test_streaming_update_is_bit_identical():
@@ -108,6 +117,13 @@ def test_full_size_cfg4_checksum():
         expect = torch.where(2 * rem > 600, q + 1, q)
         not_tie = 2 * rem != 600
         assert torch.equal(mean_u8[r][not_tie].to(torch.int64), expect[not_tie])
+        # the ties of this row, if any (the sum of 600 noise terms of sigma 3 rarely reaches +-300: a handful in the
+        # image), against the oracle's sequential recurrence
+        w_idx, c_idx = torch.nonzero(~not_tie, as_tuple=True)
+        if len(w_idx):
+            sub = host(frames[:, r][:, w_idx, c_idx])                      # (600, K)
+            o = ow.welford([f.reshape(-1, 1, 1) for f in sub])
+            assert np.array_equal(host(mean_u8[r][w_idx, c_idx]), o["mean_u8"].reshape(-1))
     crop = host(frames[:, 500:502, 100:164])
     o = ow.welford(list(crop))
     assert np.array_equal(host(mean_u8[500:502, 100:164]), o["mean_u8"])
