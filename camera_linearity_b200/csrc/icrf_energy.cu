@@ -97,8 +97,12 @@ __device__ __forceinline__ void build_curve(const cl_icrf_problem& prob, const d
         const bool masked = v < lo || v > hi;                                                   // :97-98
         const int64_t at = ((int64_t)(s / kGroup) * D + d) * kGroup + (s % kGroup);
         if (uniform_masks(prob)) {          // masked entries contribute |0 * x - 1| = 1, subtracted by the kernel
-            tables[at] = masked ? 0.0 : v;
-            tables[(int64_t)prob.n_candidates * D + at] = masked ? 0.0 : 1.0 / v;
+            // A gated candidate's energy is +inf whatever its sums are, and its curve need not be monotone, so its
+            // own mask could zero entries INSIDE the DN range; the weighted pixel loop would take those for
+            // zero-variance pairs and walk its pixels a second time.  It gets the benign table 1 on [lower, upper].
+            const bool inside = d >= prob.lower && d <= prob.upper;
+            tables[at] = bad ? (inside ? 1.0 : 0.0) : (masked ? 0.0 : v);
+            tables[(int64_t)prob.n_candidates * D + at] = bad ? (inside ? 1.0 : 0.0) : (masked ? 0.0 : 1.0 / v);
         } else {
             const double m = masked ? __longlong_as_double(0x7ff8000000000000LL) : v;
             tables[at] = m;
@@ -161,7 +165,7 @@ __device__ __forceinline__ void load_pixel(PixelData<N, USE_STD>& d, const uint8
 
 // UNIFORM (lower >= 1): `vmask` bit k = exposure k of this pixel is inside [lower, upper] (warp-uniform)
 template <int N, bool USE_STD, int P>
-__device__ __forceinline__ uint32_t accumulate_pixel_uniform(const PixelData<N, USE_STD>& d, uint32_t vmask,
+__device__ __forceinline__ void accumulate_pixel_uniform(const PixelData<N, USE_STD>& d, uint32_t vmask,
                                                          const double* __restrict__ tabI,
                                                          const double* __restrict__ tabR, int lane,
                                                          const ExposureScales& sc, double (&num)[P], double (&den)[P]) {
@@ -177,7 +181,6 @@ __device__ __forceinline__ uint32_t accumulate_pixel_uniform(const PixelData<N, 
         if (USE_STD && k < N - 1) C[USE_STD ? k : 0] = d.sg[USE_STD ? k : 0] * sc.inv_t[k];
     }
     int q = 0;
-    uint32_t odd = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
 #pragma unroll
@@ -192,25 +195,24 @@ __device__ __forceinline__ uint32_t accumulate_pixel_uniform(const PixelData<N, 
                 const double var = fma(t1, t1, t2 * t2);
                 // pair inside the range (warp-uniform bit) and sigma != 0 (:134); |d| is finite here.  The weight is
                 // the main path of rsqrt() without its range test and slow-path branch: ten of those per pixel
-                // fenced the schedule (0.375 -> 0.333 ms per population without them; a rare-case branch per PAIR
-                // was slower than the library call, 0.401; one per PIXEL 0.361).  A pair that is out of range or whose
-                // variance is not a normal positive number gets weight 0 and adds exact zeros; the caller notes it
-                // and revisits its pixels after the loop (fix_pixel_uniform).
+                // fenced the schedule (same-box A/B, ms per population: library rsqrt 0.375; main path with a
+                // rare-case branch per PAIR 0.401, per PIXEL 0.361, with a per-pair "odd" flag and the rare cases
+                // after the loop 0.361; no bookkeeping in the loop at all 0.332).  A pair that is out of range or
+                // whose variance is not a normal positive number gets weight 0 and adds exact zeros.  Whether such
+                // a pair CAN exist is decided before the loop from the sigmas alone (see `wild` in the kernel).
                 const bool in_range = (vmask >> i) & (vmask >> j) & 1u;
                 const bool fast = in_range && normal_positive(var);
                 double w = rsqrt_main_path(var);
                 w = fast ? w : 0.0;
-                odd |= (uint32_t)(in_range && !fast);
                 num[q] = fma(a, w, num[q]);
                 den[q] += w;
             }
         }
     }
-    return odd;
 }
 
-// Second visit of a pixel that had a pair inside the range whose variance is not a normal positive number: zero / NaN
-// (the pair is skipped, :134) or denormal (library rsqrt).  Only those pairs add something here.
+// Second visit of a pixel (CTAs whose sigmas are `wild` only): pairs inside the range whose variance is not a normal
+// positive number -- zero / NaN (the pair is skipped, :134) or denormal (library rsqrt).  Only the latter add something.
 template <int N, int P>
 __device__ __forceinline__ void fix_pixel_uniform(const PixelData<N, true>& d, uint32_t vmask,
                                                   const double* __restrict__ tabI, const double* __restrict__ tabR,
@@ -350,15 +352,35 @@ energy_partial_kernel(const double* __restrict__ tables, int D, int S, const uin
         tabI[i] = srcI[i];
         tabR[i] = srcR[i];
     }
-    __syncthreads();
+    const int64_t first = (int64_t)blockIdx.x * px_per_cta;
+    const int64_t last = min(n_pixels, first + px_per_cta);
+    // `wild`: can a pair of this CTA's pixels have a variance that is not a normal positive number?  With every
+    // sigma in [2^-332, 2^332], exposure-time ratios in [1e-50, 1e50] and 1/I >= 1 (a candidate that passes the
+    // gates has I <= 1; a gated one has the table 1) the first variance term is >= (2^-332 * 1e-50)^2 ~ 1e-300:
+    // normal, or +inf by overflow, whose exact weight is the 0 the loop adds.  So one streaming look at the CTA's
+    // sigmas (L2-hot for the loop that follows) replaces any bookkeeping inside the loop; a wild CTA -- a zero, NaN,
+    // negative or denormal-scale sigma somewhere -- walks its pixels a second time with the exact routine.
+    int wild = 0;
+    if (USE_STD && UNIFORM) {
+        const double* sdc = sd + first * N;
+        const int64_t count = (last - first) * N;
+        for (int64_t e = threadIdx.x; e < count; e += WARPS * 32)
+            wild |= !((uint32_t)(__double2hiint(__ldg(sdc + e)) - 0x2B300000) < 0x29800000u);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) {
+                const double r = sc.t[j] * sc.inv_t[i];
+                wild |= !(r >= 1e-50 && r <= 1e50);
+            }
+    }
+    wild = __syncthreads_or(wild);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double num[P], den[P];
     int cnt[P];
 #pragma unroll
     for (int q = 0; q < P; ++q) { num[q] = 0.0; den[q] = 0.0; cnt[q] = 0; }
-    const int64_t first = (int64_t)blockIdx.x * px_per_cta;
-    const int64_t last = min(n_pixels, first + px_per_cta);
     int64_t px = first + warp;
     PixelData<N, USE_STD> cur, nxt;
     if (px < last) load_pixel<N, USE_STD>(cur, dn, sd, px, D);
@@ -376,17 +398,16 @@ energy_partial_kernel(const double* __restrict__ tables, int D, int S, const uin
         // two pixels per iteration (px and px + WARPS): two independent gather -> multiply -> FMA -> add chains in
         // flight per warp -- with 4 warps per scheduler one chain left the issue slots ~25 % empty
         if (USE_STD) {                  // FP64 bound: one pixel per iteration (the second window only costs registers)
-            uint32_t odd = 0;
             for (; px < last; px += WARPS) {
                 if (px + WARPS < last) load_pixel<N, USE_STD>(nxt, dn, sd, px + WARPS, D);     // prefetch
                 uint32_t vmask = 0;
 #pragma unroll
                 for (int k = 0; k < N; ++k) vmask |= ((uint32_t)(cur.bin[k] - lower) <= span ? 1u : 0u) << k;
-                odd |= accumulate_pixel_uniform<N, USE_STD, P>(cur, vmask, tabI, tabR, lane, sc, num, den);
+                accumulate_pixel_uniform<N, USE_STD, P>(cur, vmask, tabI, tabR, lane, sc, num, den);
                 cur = nxt;
             }
             if constexpr (USE_STD) {
-                if (odd) {              // rare: some pair had a zero / NaN / denormal variance -- walk the pixels again
+                if (wild) {             // rare: zero / NaN / denormal-scale sigmas in this CTA -- walk the pixels again
                     for (px = first + warp; px < last; px += WARPS) {
                         load_pixel<N, USE_STD>(cur, dn, sd, px, D);
                         uint32_t vmask = 0;
