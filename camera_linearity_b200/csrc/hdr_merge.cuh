@@ -247,6 +247,22 @@ __device__ __forceinline__ void flat_apply(double& val, double& sd_out, double v
     val = vr * m;
 }
 
+// flat_apply with sqrt()'s main path (common.cuh): same bits wherever the radicand is on it; returns false when the
+// caller must have the sample recomputed (a zero radicand is selected and fine).
+__device__ __forceinline__ bool flat_apply_main_path(double& val, double& sd_out, double var, double rf, double fs,
+                                                     double m, double ms) {
+    const double vr = val * rf;
+    const double k1 = rf * m;
+    const double t2 = ((vr * rf) * fs) * m;
+    const double t3 = vr * ms;
+    const double rad = fma(var, k1 * k1, fma(t2, t2, t3 * t3));
+    bool ok;
+    const double root = sqrt_main_path(rad, ok);
+    sd_out = ok ? root : 0.0;
+    val = vr * m;
+    return ok || rad == 0.0;
+}
+
 // 1 / (dn / 255) for 8-bit flats, correctly rounded at compile time (identical to the two device
 // divisions it replaces); dn = 0 -> +inf like IEEE division.
 struct RecipTable {

@@ -249,17 +249,20 @@ merge_stream_lut_kernel(const __grid_constant__ MergeParams p, const SLutLayout 
                 if (lane == 0 && consumed_nonneg(A0, A1, A2)) mbar_arrive(&empty[s]);
                 if (++s == stages) { s = 0; phase ^= 1; }
             }
+            // 1 / S and the square roots: the library's main paths (see merge_stream_kernel); a sample off them joins
+            // the cancelled ones on the work list
+#ifndef CL_STREAM_LIBRARY_MATH
+            bool k0, k1, k2;
+            const double r0 = rcp_main_path(S0, k0), r1 = rcp_main_path(S1, k1), r2 = rcp_main_path(S2, k2);
+#else
+            const bool k0 = true, k1 = true, k2 = true;
             const double r0 = 1.0 / S0, r1 = 1.0 / S1, r2 = 1.0 / S2;
+#endif
             double v0 = av0 * r0, v1 = av1 * r1, v2 = av2 * r2;
             const double q0 = expanded_variance(A0, B0, C0, r0), q1 = expanded_variance(A1, B1, C1, r1),
                          q2 = expanded_variance(A2, B2, C2, r2);
-            // samples whose expansion cancelled go to the exact two-pass formula (work list -> merge_fixup_kernel)
-            const bool c0 = q0 < kStreamCancel * A0, c1f = q1 < kStreamCancel * A1, c2f = q2 < kStreamCancel * A2;
-            if (__any_sync(0xffffffffu, c0 | c1f | c2f)) {
-                flag_sample(p, c0, (uint32_t)i0 + 0u, lane);
-                flag_sample(p, c1f, (uint32_t)i0 + 1u, lane);
-                flag_sample(p, c2f, (uint32_t)i0 + 2u, lane);
-            }
+            bool c0 = q0 < kStreamCancel * A0 || !k0, c1f = q1 < kStreamCancel * A1 || !k1,
+                 c2f = q2 < kStreamCancel * A2 || !k2;
             double u0, u1, u2;
             if (has_flat) {
                 double rf0, rf1, rf2;
@@ -279,11 +282,31 @@ merge_stream_lut_kernel(const __grid_constant__ MergeParams p, const SLutLayout 
                     rf2 = flat_recip(p.flat, p.flat_bytes, i0 + 2, p.max_dn);
                 }
                 constexpr int c1 = MONO ? 0 : 1, c2 = MONO ? 0 : 2;
+#ifndef CL_STREAM_LIBRARY_MATH
+                c0 |= !flat_apply_main_path(v0, u0, (q0 * r0) * r0, rf0, f0, p.flat_means[0], p.flat_means[kCt + 0]);
+                c1f |= !flat_apply_main_path(v1, u1, (q1 * r1) * r1, rf1, f1, p.flat_means[c1], p.flat_means[kCt + c1]);
+                c2f |= !flat_apply_main_path(v2, u2, (q2 * r2) * r2, rf2, f2, p.flat_means[c2], p.flat_means[kCt + c2]);
+#else
                 flat_apply(v0, u0, (q0 * r0) * r0, rf0, f0, p.flat_means[0], p.flat_means[kCt + 0]);
                 flat_apply(v1, u1, (q1 * r1) * r1, rf1, f1, p.flat_means[c1], p.flat_means[kCt + c1]);
                 flat_apply(v2, u2, (q2 * r2) * r2, rf2, f2, p.flat_means[c2], p.flat_means[kCt + c2]);
+#endif
             } else {
+#ifndef CL_STREAM_LIBRARY_MATH
+                bool s0, s1, s2;
+                const double t0 = sqrt_main_path(q0, s0), t1 = sqrt_main_path(q1, s1), t2 = sqrt_main_path(q2, s2);
+                u0 = (s0 ? t0 : 0.0) * r0; u1 = (s1 ? t1 : 0.0) * r1; u2 = (s2 ? t2 : 0.0) * r2;
+                c0 |= !(s0 || q0 == 0.0); c1f |= !(s1 || q1 == 0.0); c2f |= !(s2 || q2 == 0.0);
+#else
                 u0 = sqrt(q0) * r0; u1 = sqrt(q1) * r1; u2 = sqrt(q2) * r2;
+#endif
+            }
+            // samples whose expansion cancelled (or that left a main path) go to the exact formula (work list ->
+            // merge_fixup_kernel)
+            if (__any_sync(0xffffffffu, c0 | c1f | c2f)) {
+                flag_sample(p, c0, (uint32_t)i0 + 0u, lane);
+                flag_sample(p, c1f, (uint32_t)i0 + 1u, lane);
+                flag_sample(p, c2f, (uint32_t)i0 + 2u, lane);
             }
             __stcs(p.out_val + i0 + 0, v0); __stcs(p.out_val + i0 + 1, v1); __stcs(p.out_val + i0 + 2, v2);
             __stcs(p.out_std + i0 + 0, u0); __stcs(p.out_std + i0 + 1, u1); __stcs(p.out_std + i0 + 2, u2);
